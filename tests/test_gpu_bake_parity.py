@@ -1,0 +1,161 @@
+"""GPU parity, bake level: CameraProjection / uv_* against the oracle's restatement of uv.py and
+projection.py.  Booleans (uv_mask, validity) are compared exactly away from the thresholds: a texel
+whose deciding quantity lies within 1e-5 relative of a threshold may legitimately flip."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import worldrenderer_b200 as wr
+from oracle import render_oracle
+from test_gpu_render_parity import make_mesh
+from worldrenderer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _setup(device, freq=8, views=(96, 96), seed=1, old_texture=True, uv_size=128):
+    v, f = cases.icosphere_mesh(freq)
+    mesh = make_mesh(v, f, device, with_uv=True, tex_size=uv_size, seed=seed)
+    if not old_texture:
+        mesh.texture = torch.zeros_like(mesh.texture)
+    cam = cases.canonical_cameras(device=device)
+    images = synth.view_images(6, views[0], views[1], seed=seed)
+    return mesh, cam, images
+
+
+def _oracle_bake(mesh, cam, images, uv_size, masks=None, **kw):
+    return render_oracle.camera_projection(
+        images, mesh.v_pos.cpu().numpy(), mesh.t_pos_idx.cpu().numpy().astype(np.int32), mesh.v_nrm.cpu().numpy(),
+        mesh.t_pos_idx.cpu().numpy().astype(np.int32), mesh.v_tex.cpu().numpy(),
+        mesh.t_tex_idx.cpu().numpy().astype(np.int32), mesh.texture.cpu().numpy(), cam.mvp_mtx.cpu().numpy(),
+        cam.w2c.cpu().numpy(), uv_size, masks=masks, **kw)
+
+
+def _near_threshold(ref, aoi_thr, dg_thr, eps=1e-3):
+    geo = ref["geo"]
+    near = np.abs(geo["uv_pos_error"] - eps) < 2e-5 * eps + 1e-7
+    near |= np.abs(geo["uv_aoi_cos"] - aoi_thr) < 2e-5
+    if dg_thr is not None:
+        near |= np.abs(geo["uv_depth_grad"] - dg_thr) < 2e-5 * max(1.0, dg_thr)
+    return near.any(0)
+
+
+def test_uv_precompute(wr_ctx):
+    mesh, cam, images = _setup(wr_ctx.device)
+    pre = wr.uv_precompute(wr_ctx, mesh, 128, 128)
+    ref = render_oracle.uv_precompute(mesh.v_pos.cpu().numpy(), mesh.t_pos_idx.cpu().numpy(), mesh.v_tex.cpu().numpy(),
+                                      mesh.t_tex_idx.cpu().numpy(), 128, 128)
+    np.testing.assert_array_equal(pre.uv_mask.cpu().numpy(), ref["uv_mask"])
+    np.testing.assert_allclose(pre.uv_pos.cpu().numpy(), ref["uv_pos"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("aoi_thr,dg_thr,alpha,use_vw", [(0.2, 0.1, 3.0, True), (-1.0, None, 3.0, True), (0.3, 0.1, 6.0, False)])
+def test_camera_projection_fused(wr_ctx, aoi_thr, dg_thr, alpha, use_vw):
+    mesh, cam, images = _setup(wr_ctx.device)
+    proj = wr.CameraProjection(pb_backend=None, bg_remover=None, device=str(wr_ctx.device), context_type="cuda")
+    vw = torch.tensor([1.0, 0.5, 1.0, 2.0, 1.0, 1.0]) if use_vw else None
+    out = proj(torch.from_numpy(images), mesh, cam, uv_size=128, poisson_blending=False, uv_padding=False,
+               depth_grad_dilation=5, uv_exp_blend_alpha=alpha, uv_exp_blend_view_weight=vw,
+               aoi_cos_valid_threshold=aoi_thr, depth_grad_threshold=dg_thr, iou_rejection_threshold=None,
+               return_dict=True)
+    ref = _oracle_bake(mesh, cam, images, 128, aoi_cos_valid_threshold=aoi_thr, depth_grad_threshold=dg_thr,
+                       uv_exp_blend_alpha=alpha, uv_exp_blend_view_weight=None if vw is None else vw.numpy(),
+                       depth_grad_dilation=5)
+    np.testing.assert_allclose(out.uv_aoi_cos.cpu().numpy(), ref["uv_aoi_cos"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.uv_depth_grad.cpu().numpy(), ref["uv_depth_grad"], rtol=RTOL, atol=2e-5)
+    stable = ~_near_threshold(ref, aoi_thr, dg_thr)
+    assert stable.mean() > 0.99
+    got_mask = out.uv_proj_mask.cpu().numpy()
+    np.testing.assert_array_equal(got_mask[stable], ref["uv_proj_mask"][stable])
+    got = out.uv_proj.cpu().numpy()
+    np.testing.assert_allclose(got[stable], ref["uv_proj"][stable], rtol=1e-4, atol=2e-6)
+    assert got_mask.sum() > 0.3 * ref["pre"]["uv_mask"].sum()
+    # plain return forms (projection.py:190-204)
+    t = proj(torch.from_numpy(images), mesh, cam, uv_size=128, poisson_blending=False, uv_padding=False,
+             uv_exp_blend_alpha=alpha, uv_exp_blend_view_weight=vw, aoi_cos_valid_threshold=aoi_thr,
+             depth_grad_threshold=dg_thr, iou_rejection_threshold=None)
+    assert torch.equal(t, out.uv_proj)
+    t2, m2 = proj(torch.from_numpy(images), mesh, cam, uv_size=128, poisson_blending=False, uv_padding=False,
+                  uv_exp_blend_alpha=alpha, uv_exp_blend_view_weight=vw, aoi_cos_valid_threshold=aoi_thr,
+                  depth_grad_threshold=dg_thr, iou_rejection_threshold=None, return_uv_projection_mask=True)
+    assert torch.equal(m2, out.uv_proj_mask)
+
+
+def test_masks_and_iou_rejection(wr_ctx):
+    mesh, cam, images = _setup(wr_ctx.device)
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    rendered = wr.render(wr_ctx, mesh, cam, 96, 96, render_attr=False).mask.float()
+    out = proj(torch.from_numpy(images), mesh, cam, masks=rendered, uv_size=128, poisson_blending=False,
+               uv_padding=False, return_dict=True)
+    ref = _oracle_bake(mesh, cam, images, 128, masks=rendered.cpu().numpy())
+    assert out is not None and ref is not None
+    stable = ~_near_threshold(ref, 0.3, 0.1)
+    near_mask = (np.abs(ref["attr"]["uv_mask_proj"] - 0.9) < 1e-4).any(0)
+    stable &= ~near_mask
+    np.testing.assert_array_equal(out.uv_proj_mask.cpu().numpy()[stable], ref["uv_proj_mask"][stable])
+    np.testing.assert_allclose(out.uv_proj.cpu().numpy()[stable], ref["uv_proj"][stable], rtol=1e-4, atol=2e-6)
+    bad = torch.zeros_like(rendered)
+    bad[:, :10, :10] = 1
+    assert proj(torch.from_numpy(images), mesh, cam, masks=bad, uv_size=128, poisson_blending=False,
+                uv_padding=False) is None
+
+
+def test_stepwise_api_matches_oracle(wr_ctx):
+    mesh, cam, images = _setup(wr_ctx.device)
+    pre = wr.uv_precompute(wr_ctx, mesh, 128, 128)
+    geo = wr.uv_render_geometry(wr_ctx, mesh, cam, 96, 96, pre, compute_depth_grad=True, depth_grad_dilation=3)
+    attr = wr.uv_render_attr(torch.from_numpy(images), geo)
+    v, f = mesh.v_pos.cpu().numpy(), mesh.t_pos_idx.cpu().numpy().astype(np.int32)
+    rpre = render_oracle.uv_precompute(v, f, mesh.v_tex.cpu().numpy(), mesh.t_tex_idx.cpu().numpy(), 128, 128)
+    rgeo = render_oracle.uv_render_geometry(v, f, mesh.v_nrm.cpu().numpy(), f, cam.mvp_mtx.cpu().numpy(),
+                                            cam.w2c.cpu().numpy(), 96, 96, rpre, True, 3)
+    rattr = render_oracle.uv_render_attr(images, rgeo)
+    np.testing.assert_array_equal(geo.view_mask.cpu().numpy(), rgeo["view_mask"])
+    inside = rpre["uv_mask"]
+    for name in ["uv_pos_proj", "uv_pos_error", "uv_aoi_cos", "uv_pos_ndc", "uv_depth_grad"]:
+        np.testing.assert_allclose(getattr(geo, name).cpu().numpy()[:, inside], rgeo[name][:, inside], rtol=1e-4,
+                                   atol=2e-5, err_msg=name)
+    for name in ["view_aoi_cos", "view_position", "view_normal", "view_depth"]:
+        np.testing.assert_allclose(getattr(geo, name).cpu().numpy(), rgeo[name], rtol=RTOL, atol=ATOL, err_msg=name)
+    np.testing.assert_allclose(geo.view_depth_grad[:, 0].cpu().numpy(), rgeo["view_depth_grad"], rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(attr.uv_attr_proj.cpu().numpy()[:, inside], rattr["uv_attr_proj"][:, inside],
+                               rtol=1e-4, atol=2e-6)
+    blend = wr.uv_blend(pre, geo, attr, uv_validity_strategy=wr.SimpleUVValidityStrategy(aoi_cos_thresh=0.2, depth_grad_thresh=0.1),
+                        uv_blend_weight_strategy=wr.ExponentialBlend(alpha=3.0), do_uv_padding=False)
+    # the step-by-step blend and the fused kernel agree with each other
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    fused = proj(torch.from_numpy(images), mesh, cam, uv_size=128, poisson_blending=False, uv_padding=False,
+                 depth_grad_dilation=3, uv_exp_blend_alpha=3.0, aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
+                 iou_rejection_threshold=None, return_dict=True)
+    assert torch.equal(fused.uv_proj_mask, blend.uv_valid_mask_blend)
+    torch.testing.assert_close(fused.uv_proj, blend.uv_attr_blend, rtol=1e-4, atol=2e-6)
+
+
+def test_accumulate_then_finalize_equals_fused(wr_ctx):
+    """The multi-GPU decomposition on one device: two view shards accumulated, then finalised."""
+    from worldrenderer_b200.uv import fused_unproject, fused_view_maps, uv_finalize
+    mesh, cam, images = _setup(wr_ctx.device)
+    pre = wr.uv_precompute(wr_ctx, mesh, 128, 128)
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    kw = dict(aoi_cos_thresh=0.2, depth_grad_thresh=0.1, alpha=3.0)
+    _, geo, att = fused_view_maps(wr_ctx, mesh, cam, img, 96, 96, 5)
+    full, full_any, _, _, _ = fused_unproject(wr_ctx, pre, cam, 96, 96, geo, att, **kw)
+    accum = None
+    for sl in [slice(0, 2), slice(2, 6)]:
+        _, g, a = fused_view_maps(wr_ctx, mesh, cam[sl], img[sl], 96, 96, 5)
+        _, _, accum, _, _ = fused_unproject(wr_ctx, pre, cam[sl], 96, 96, g, a, accumulate_only=True, accum=accum, **kw)
+    out, any_ = uv_finalize(wr_ctx, accum, pre.uv_attr)
+    assert torch.equal(any_, full_any)
+    torch.testing.assert_close(out, full, rtol=1e-5, atol=1e-6)
+
+
+def test_unsupported_options_raise(wr_ctx):
+    mesh, cam, images = _setup(wr_ctx.device)
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    with pytest.raises(NotImplementedError):
+        proj(torch.from_numpy(images), mesh, cam, uv_size=64)  # defaults ask for Poisson blending + padding
+    with pytest.raises(NotImplementedError):
+        proj(torch.from_numpy(images), mesh, cam, uv_size=64, poisson_blending=False, uv_padding=True)

@@ -1,0 +1,179 @@
+"""GPU parity, render() level: the fused wr_render pipeline against the oracle's restatement of
+render.py:220-286 (oracle/render_oracle.py, pinned to the reference's own Python by tests/golden).
+
+Bar: mask / triangle id bit-exact; pos, normal, depth within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import worldrenderer_b200 as wr
+from oracle import render_oracle
+from oracle.render_oracle import DepthSpec
+from worldrenderer_b200.render import render_geometry_raw
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def make_mesh(v, f, device, with_uv=False, tex_size=32, seed=0):
+    mesh = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f, dtype=torch.int64))
+    mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
+    if with_uv:
+        from worldrenderer_b200 import synth
+        vt, ft = synth.cell_atlas_uv(f.shape[0])
+        mesh.v_tex = torch.tensor(vt, dtype=torch.float32)
+        mesh.t_tex_idx = torch.tensor(ft, dtype=torch.int64)
+        rng = np.random.default_rng(seed)
+        mesh.texture = torch.tensor(rng.uniform(0, 1, (tex_size, tex_size, 3)), dtype=torch.float32)
+    mesh.to(device)
+    return mesh
+
+
+STRATEGIES = [
+    (wr.DepthControlNetNormalization(), DepthSpec("controlnet")),
+    (wr.DepthControlNetNormalization(far_clip=0.1, near_clip=0.9, bg_value=0.3), DepthSpec("controlnet", far_clip=0.1, near_clip=0.9, bg_value=0.3)),
+    (wr.Zero123PlusPlusNormalization(), DepthSpec("zero123pp")),
+    (wr.SimpleNormalization(), DepthSpec("simple", scale=1.0, offset=-1.0, clamp=True)),
+    (wr.SimpleNormalization(scale=1.0, offset=0.0, clamp=False, bg_value=1e2), DepthSpec("simple", scale=1.0, offset=0.0, clamp=False, bg_value=1e2)),
+    (None, DepthSpec("none")),
+]
+
+
+def _oracle(mesh, cam, H, W, spec, with_attr=False, filt="linear"):
+    kw = {}
+    if with_attr:
+        kw = dict(v_tex=mesh.v_tex.cpu().numpy(), tri_tex=mesh.t_tex_idx.cpu().numpy().astype(np.int32),
+                  texture=mesh.texture.cpu().numpy(), texture_filter_mode=filt)
+    return render_oracle.render(mesh.v_pos.cpu().numpy(), mesh.t_pos_idx.cpu().numpy().astype(np.int32),
+                                cam.mvp_mtx.cpu().numpy(), cam.w2c.cpu().numpy(), H, W,
+                                v_nrm=mesh.v_nrm.cpu().numpy(), depth=spec, **kw)
+
+
+def _compare(out, ref, ids=None):
+    np.testing.assert_array_equal(out.mask.cpu().numpy(), ref["mask"])
+    if ids is not None:
+        np.testing.assert_array_equal(ids.cpu().numpy(), ref["tri_id"])
+    np.testing.assert_allclose(out.pos.cpu().numpy(), ref["pos"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.normal.cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out.depth.cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("strategy,spec", STRATEGIES)
+def test_icosphere_canonical_rig(wr_ctx, strategy, spec):
+    v, f = cases.icosphere_mesh(10)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    out = wr.render(wr_ctx, mesh, cam, 160, 160, render_attr=False, depth_normalization_strategy=strategy)
+    assert out.mask.dtype == torch.bool and out.depth.shape == (6, 160, 160) and out.pos.shape == (6, 160, 160, 3)
+    _compare(out, _oracle(mesh, cam, 160, 160, spec))
+
+
+def test_tri_ids_and_rast_fused(wr_ctx):
+    v, f = cases.terrain_mesh(128, 64)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    for cam in [cases.canonical_cameras(device=wr_ctx.device), cases.perspective_cameras(device=wr_ctx.device),
+                cases.inside_cameras(device=wr_ctx.device)]:
+        raw = render_geometry_raw(wr_ctx, mesh, cam, 200, 264, want_tri_id=True, want_rast=True,
+                                  depth_normalization_strategy=wr.DepthControlNetNormalization())
+        ref = _oracle(mesh, cam, 200, 264, DepthSpec("controlnet"))
+        np.testing.assert_array_equal(raw["tri_id"].cpu().numpy(), ref["tri_id"])
+        np.testing.assert_array_equal(raw["mask"].cpu().numpy(), ref["mask"])
+        np.testing.assert_allclose(raw["rast"].cpu().numpy(), ref["rast"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(raw["pos"].cpu().numpy(), ref["pos"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(raw["normal"].cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(raw["depth"].cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
+
+
+def test_custom_strategy_and_backgrounds(wr_ctx):
+    v, f = cases.icosphere_mesh(6)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+
+    class Halve(wr.DepthNormalizationStrategy):
+        def __init__(self):
+            pass
+
+        def __call__(self, depth, mask):
+            return depth * 0.5
+
+    out = wr.render(wr_ctx, mesh, cam, 64, 80, render_attr=False, depth_normalization_strategy=Halve(),
+                    normal_background=torch.tensor([0.5, 0.25, 1.0]))
+    ref = _oracle(mesh, cam, 64, 80, DepthSpec("none"))
+    np.testing.assert_allclose(out.depth.cpu().numpy(), ref["depth"] * np.float32(0.5), rtol=RTOL, atol=ATOL)
+    n = out.normal.cpu().numpy()
+    assert np.allclose(n[~ref["mask"]], [0.5, 0.25, 1.0])
+    np.testing.assert_allclose(n[ref["mask"]], ref["normal"][ref["mask"]], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("filt", ["linear", "nearest"])
+def test_render_attr(wr_ctx, filt):
+    v, f = cases.icosphere_mesh(6)
+    mesh = make_mesh(v, f, wr_ctx.device, with_uv=True)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    out = wr.render(wr_ctx, mesh, cam, 128, 128, render_attr=True, texture_filter_mode=filt, attr_background=0.25)
+    ref = _oracle(mesh, cam, 128, 128, DepthSpec("controlnet"), with_attr=True, filt=filt)
+    ref_attr = np.where(ref["mask"][..., None], ref["attr"], np.float32(0.25))
+    np.testing.assert_allclose(out.attr.cpu().numpy(), ref_attr, rtol=RTOL, atol=ATOL)
+    _compare(out, ref)
+
+
+def test_vertex_normals_match_oracle(wr_ctx):
+    v, f = cases.terrain_mesh(64, 48)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    ref = render_oracle.vertex_normals(v, f)
+    # float atomics: sum order differs from the CPU loop, so tolerance (not bit) parity
+    np.testing.assert_allclose(mesh.v_nrm.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_single_view_indexing_and_no_cpu_path(wr_ctx):
+    v, f = cases.icosphere_mesh(4)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    full = wr.render(wr_ctx, mesh, cam, 48, 48, render_attr=False)
+    one = wr.render(wr_ctx, mesh, cam[2], 48, 48, render_attr=False)
+    assert one.mask.shape == (1, 48, 48)
+    assert torch.equal(one.mask[0], full.mask[2]) and torch.equal(one.pos[0], full.pos[2])
+    cpu_mesh = make_mesh(v, f, "cpu")
+    with pytest.raises(RuntimeError):
+        wr.render(wr_ctx, cpu_mesh, cam, 48, 48, render_attr=False)
+    with pytest.raises(RuntimeError):
+        wr.NVDiffRastContextWrapper("cpu", "cuda")
+    with pytest.raises(NotImplementedError):
+        wr.NVDiffRastContextWrapper(str(wr_ctx.device), "vulkan")
+
+
+def test_full_size_properties_1m_faces(wr_ctx):
+    """BASELINE config B at full size (1M faces, 6 views, 768^2): properties that need no oracle run."""
+    from worldrenderer_b200 import synth
+    v, f = synth.terrain(1000, 500, 0)
+    v = v / np.abs(v).max() * 0.5
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1).astype(np.float32)
+    mesh = make_mesh(v, f.astype(np.int32), wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    raw = render_geometry_raw(wr_ctx, mesh, cam, 768, 768, want_tri_id=True, want_rast=True,
+                              depth_normalization_strategy=wr.DepthControlNetNormalization())
+    raw2 = render_geometry_raw(wr_ctx, mesh, cam, 768, 768, want_tri_id=True, want_rast=True,
+                               depth_normalization_strategy=wr.DepthControlNetNormalization())
+    ids = raw["tri_id"]
+    assert torch.equal(ids, raw2["tri_id"]) and torch.equal(raw["pos"], raw2["pos"])  # deterministic
+    assert int(ids.max()) < f.shape[0] and int(ids.min()) == -1
+    assert torch.equal(raw["mask"], ids >= 0)
+    # top view (elevation 89.99) of a height field covers its whole footprint: a filled rectangle
+    m = raw["mask"][4]
+    rows = m.any(1).nonzero().flatten()
+    cols = m.any(0).nonzero().flatten()
+    assert bool(m[rows.min():rows.max() + 1, cols.min():cols.max() + 1].all())
+    # barycentrics of covered pixels are a partition of unity and positions lie inside the mesh bounds
+    r = raw["rast"][raw["mask"]]
+    assert float((r[:, 0] + r[:, 1]).max()) <= 1.0 + 1e-5
+    p = raw["pos"][raw["mask"]]
+    assert float(p.abs().max()) <= 0.5 + 1e-6
+    n = raw["normal"][raw["mask"]]
+    assert torch.allclose(n.norm(dim=-1), torch.ones_like(n[:, 0]), atol=1e-5)
+    # the operator path (clip positions by torch.matmul is NOT used: same fixed-order transform) agrees
+    # with the fused path on ids when fed the fused path's own clip positions
+    d = raw["depth"]
+    assert float(d[raw["mask"]].min()) >= 0.25 - 1e-6 and float(d.max()) <= 1.0 + 1e-6
+    assert float(d[~raw["mask"]].abs().max()) == 0.0

@@ -1,0 +1,84 @@
+// Context, scratch and status plumbing of libwr_b200 (replaces dr.RasterizeCudaContext /
+// dr.RasterizeGLContext, render.py:31-37).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+extern "C" const char *wr_status_string(int status)
+{
+    switch (status) {
+    case WR_OK: return "ok";
+    case WR_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case WR_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case WR_ERR_CUDA: return "CUDA error";
+    case WR_ERR_NO_DEVICE: return "no usable CUDA device";
+    case WR_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown status";
+    }
+}
+
+extern "C" int wr_version(void) { return 100; }
+
+extern "C" const char *wr_ctx_last_error(const wr_ctx *ctx) { return ctx ? ctx->last_error : ""; }
+
+extern "C" uint64_t wr_ctx_scratch_bytes(const wr_ctx *ctx) { return ctx ? (uint64_t)ctx->scratch_bytes : 0; }
+
+int wr_set_cuda_error(wr_ctx *ctx, cudaError_t e, const char *where)
+{
+    if (ctx) snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", where, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? WR_ERR_OUT_OF_MEMORY : WR_ERR_CUDA;
+}
+
+extern "C" int wr_ctx_create(int device, wr_ctx **out)
+{
+    if (!out) return WR_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return WR_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return WR_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WR_ERR_CUDA;
+    if (prop.major != 10) return WR_ERR_NO_DEVICE;  // this library carries sm_100a code only
+    wr_ctx *ctx = static_cast<wr_ctx *>(calloc(1, sizeof(wr_ctx)));
+    if (!ctx) return WR_ERR_OUT_OF_MEMORY;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return WR_OK;
+}
+
+extern "C" void wr_ctx_destroy(wr_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->scratch) {
+        cudaSetDevice(ctx->device);
+        cudaFree(ctx->scratch);
+    }
+    free(ctx);
+}
+
+// Grow-only scratch.  Growth frees the old block with cudaFree, which waits for work in flight.
+int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream)
+{
+    (void)stream;
+    if (bytes <= ctx->scratch_bytes) return WR_OK;
+    if (ctx->scratch) {
+        cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    const size_t want = bytes + bytes / 8;  // headroom so slightly larger calls do not reallocate
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaMalloc(scratch)");
+        ctx->scratch_bytes = bytes;
+    } else {
+        ctx->scratch_bytes = want;
+    }
+    ctx->scratch = p;
+    return WR_OK;
+}

@@ -1,0 +1,95 @@
+// Shared declarations of libwr_b200 (sm_100a).  The raster contract implemented here is
+// DESIGN.md section 3; every float expression on the coverage / depth-key path is written as a
+// sequence of individually rounded binary32 operations and this library is compiled with
+// -fmad=false, so coverage and triangle ids cannot depend on FMA contraction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/wr_b200.h"
+
+#define WR_COORD_LIMIT 4194304.0f  // 2^22 sub-pixel units
+#define WR_GUARD_BAND 16.0f
+#define WR_EMPTY_PIXEL 0xFFFFFFFFFFFFFFFFull
+
+// flags of a snapped vertex
+#define WR_SV_OK 1u        // w > 0 and snapped coordinates representable
+#define WR_SV_FINITE 2u    // all four clip coordinates finite
+#define WR_SV_OC_SHIFT 8   // six outcode bits: x<-w, x>w, y<-w, y>w, z<-w, z>w
+
+#define WR_QUEUE_SLOW 0x80000000u  // queue entry flag: triangle needs geometric clipping
+
+struct __align__(16) SnapVert {
+    int x, y;        // 1/16 pixel units, origin at the viewport centre
+    float zw;        // z/w
+    uint32_t flags;
+};
+
+// Where clip-space vertices come from: a clip-space tensor (dr.rasterize) or world positions
+// plus a per-view mvp (fused render, restating utils.py:127-129 in a fixed operation order).
+struct VtxSrc {
+    const float *pos;   // clip [B,V,4] / [V,4], or world [V,3]
+    const float *mvp;   // [B,16] row major, or nullptr when pos is already clip space
+    int V;
+    int batched;        // clip mode: pos has a leading view dimension
+};
+
+__device__ __forceinline__ float4 wr_load_clip(const VtxSrc &s, int b, int v)
+{
+    if (s.mvp) {
+        const float *p = s.pos + 3 * (size_t)v;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        const float *m = s.mvp + 16 * b;
+        float4 c;
+        c.x = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+        c.y = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+        c.z = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+        c.w = ((m[12] * x + m[13] * y) + m[14] * z) + m[15];
+        return c;
+    }
+    const float4 *p = reinterpret_cast<const float4 *>(s.pos) + (s.batched ? (size_t)b * s.V : 0) + v;
+    return __ldg(p);
+}
+
+__device__ __forceinline__ uint32_t wr_depth_key(float zw)
+{
+    uint32_t u = __float_as_uint(zw);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// order-preserving float <-> uint map for atomicMin / atomicMax on floats
+__device__ __forceinline__ uint32_t wr_float_ordered(float f) { return wr_depth_key(f); }
+__device__ __forceinline__ float wr_ordered_float(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+struct wr_ctx {
+    int device;
+    int sm_count;
+    void *scratch;
+    size_t scratch_bytes;
+    char last_error[256];
+};
+
+// result of the coverage / visibility stages: packed (depth_key << 32 | triangle id) per pixel
+struct RasterResult {
+    const unsigned long long *packed;  // [B,H,W]
+    int32_t *view_stats;               // [B,4] zero-initialised ints the caller may use
+};
+
+int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream);
+int wr_set_cuda_error(wr_ctx *ctx, cudaError_t e, const char *where);
+int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
+                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream);
+
+#define WR_CHECK_LAUNCH(ctx, where)                                  \
+    do {                                                             \
+        cudaError_t e__ = cudaGetLastError();                        \
+        if (e__ != cudaSuccess) return wr_set_cuda_error(ctx, e__, where); \
+    } while (0)
+
+static inline size_t wr_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int wr_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

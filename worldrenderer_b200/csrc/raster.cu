@@ -1,0 +1,489 @@
+// Coverage + visibility for dr.rasterize (reference call sites render.py:241, uv.py:40) on sm_100a.
+//
+// Pipeline, all on one stream, no host round trip:
+//   k_snap_vertices   one thread per (view, vertex): clip transform (fused render only), perspective
+//                     divide, snap to 1/16 px, outcodes                       -> SnapVert[B,V] (16 B)
+//   k_setup_triangles one thread per (view, triangle): cull, classify by screen extent.
+//                     * small triangles (the 1M-face case: mostly sub-pixel) are rasterised in the
+//                       same thread with exact int32 edge functions and resolved with one 64-bit
+//                       atomicMin per covered sample (depth_key << 32 | id) into an L2-resident buffer
+//                     * medium / large / to-be-clipped triangles are appended to per-view queues with
+//                       one warp-aggregated atomic per warp
+//   k_raster_queue    one warp per queued triangle (medium) or 32 warps striding over 32x32-pixel
+//                     blocks with a conservative block reject (large): 8x4-pixel footprints, one sample
+//                     per lane, warp ballot to skip empty footprints, int64 edge functions
+//   k_resolve_rast    one thread per pixel: winning id -> (u, v, z/w, id+1) from the unsnapped vertices
+//
+// Contract: DESIGN.md section 3.  CPU statement of the same contract: oracle/wr_oracle.c.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSmallMaxPix = 64;       // largest pixel bbox rasterised inside the setup thread
+constexpr int kSmallMaxExtent = 1024;  // snapped extent below which int32 edge functions are exact
+constexpr int kMediumMaxPix = 16384;   // largest pixel bbox handled by a single warp
+constexpr int kLargeStripes = 32;      // warps sharing one large triangle
+
+struct RasterParams {
+    const SnapVert *sv;            // [B,V]
+    const int32_t *tri;            // [F,3] (already offset in range mode)
+    int F, V, tri_base;            // tri_base: id of tri[0] (range mode)
+    int W, H;
+    unsigned long long *depth;     // [B,H,W]
+    uint32_t *queue;               // [B,Fq]
+    int Fq;                        // queue stride (total triangle count)
+    int *counters;                 // [B,4]: 0 medium, 1 large
+};
+
+__device__ __forceinline__ int floor_div16(int a) { return a >> 4; }
+__device__ __forceinline__ int ceil_div16(int a) { return -((-a) >> 4); }
+__device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
+
+__global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, int W, int H, SnapVert *sv)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + view0;
+    if (v >= src.V) return;
+    const float4 p = wr_load_clip(src, b, v);
+    SnapVert s;
+    s.x = 0; s.y = 0; s.zw = 0.0f;
+    uint32_t flags = 0;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(p.w)) flags |= WR_SV_FINITE;
+    uint32_t oc = 0;
+    oc |= (p.x < -p.w) ? 1u : 0u;
+    oc |= (p.x > p.w) ? 2u : 0u;
+    oc |= (p.y < -p.w) ? 4u : 0u;
+    oc |= (p.y > p.w) ? 8u : 0u;
+    oc |= (p.z < -p.w) ? 16u : 0u;
+    oc |= (p.z > p.w) ? 32u : 0u;
+    flags |= oc << WR_SV_OC_SHIFT;
+    if (p.w > 0.0f) {
+        const float rw = 1.0f / p.w;
+        const float fx = (p.x * (float)(8 * W)) * rw;
+        const float fy = (p.y * (float)(8 * H)) * rw;
+        if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
+            s.x = __float2int_rn(fx);
+            s.y = __float2int_rn(fy);
+            s.zw = p.z * rw;
+            flags |= WR_SV_OK;
+        }
+    }
+    s.flags = flags;
+    reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<int4 *>(&s);
+}
+
+__device__ __forceinline__ SnapVert load_sv(const SnapVert *sv, size_t i)
+{
+    int4 r = __ldg(reinterpret_cast<const int4 *>(sv) + i);
+    return *reinterpret_cast<SnapVert *>(&r);
+}
+
+__device__ __forceinline__ void resolve_sample(unsigned long long *dst, float zw, uint32_t id)
+{
+    const unsigned long long packed = ((unsigned long long)wr_depth_key(zw) << 32) | id;
+    atomicMin(dst, packed);
+}
+
+__global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + view0;
+    const int W = P.W, H = P.H;
+    const unsigned lane = threadIdx.x & 31;
+    int push = 0;  // 0 none, 1 medium, 2 large
+    uint32_t entry = 0;
+
+    if (t < P.F) {
+        const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
+                  i2 = __ldg(P.tri + 3 * (size_t)t + 2);
+        if ((unsigned)i0 < (unsigned)P.V && (unsigned)i1 < (unsigned)P.V && (unsigned)i2 < (unsigned)P.V) {
+            const size_t vb = (size_t)b * P.V;
+            const SnapVert a = load_sv(P.sv, vb + i0), c = load_sv(P.sv, vb + i1), d = load_sv(P.sv, vb + i2);
+            const uint32_t f_and = a.flags & c.flags & d.flags;
+            if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0) {
+                if (!(f_and & WR_SV_OK)) {
+                    push = 2;
+                    entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
+                } else {
+                    int x0 = a.x, y0 = a.y, x1 = c.x, y1 = c.y, x2 = d.x, y2 = d.y;
+                    float z0 = a.zw, z1 = c.zw, z2 = d.zw;
+                    long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+                    if (area2 != 0) {
+                        const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+                        const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+                        const int ox = 8 - 8 * W, oy = 8 - 8 * H;
+                        const int c0 = max(ceil_div16(xmin - ox), 0), c1 = min(floor_div16(xmax - ox), W - 1);
+                        const int r0 = max(ceil_div16(ymin - oy), 0), r1 = min(floor_div16(ymax - oy), H - 1);
+                        if (c0 <= c1 && r0 <= r1) {
+                            const long long npix = (long long)(c1 - c0 + 1) * (r1 - r0 + 1);
+                            if (npix <= kSmallMaxPix && xmax - xmin < kSmallMaxExtent &&
+                                ymax - ymin < kSmallMaxExtent) {
+                                // ---- small triangle: rasterise here, int32 edge functions ----
+                                if (area2 < 0) {
+                                    int ti; float tf;
+                                    ti = x1; x1 = x2; x2 = ti;
+                                    ti = y1; y1 = y2; y2 = ti;
+                                    tf = z1; z1 = z2; z2 = tf;
+                                    area2 = -area2;
+                                }
+                                const int dx0 = x2 - x1, dy0 = y2 - y1;  // edge opposite vertex 0
+                                const int dx1 = x0 - x2, dy1 = y0 - y2;
+                                const int dx2 = x1 - x0, dy2 = y1 - y0;
+                                const int bias0 = top_left(dx0, dy0) ? 0 : 1;
+                                const int bias1 = top_left(dx1, dy1) ? 0 : 1;
+                                const int bias2 = top_left(dx2, dy2) ? 0 : 1;
+                                const float inv_area = 1.0f / __ll2float_rn(area2);
+                                const int px0 = 16 * c0 + ox, py0 = 16 * r0 + oy;
+                                int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
+                                int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
+                                int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
+                                unsigned long long *row = P.depth + ((size_t)b * H + r0) * W;
+                                const uint32_t id = (uint32_t)(t + P.tri_base);
+                                for (int r = r0; r <= r1; ++r) {
+                                    int e0 = e0r, e1 = e1r, e2 = e2r;
+                                    for (int cc = c0; cc <= c1; ++cc) {
+                                        if (e0 >= bias0 && e1 >= bias1 && e2 >= bias2) {
+                                            const float b0 = __int2float_rn(e0) * inv_area;
+                                            const float b1 = __int2float_rn(e1) * inv_area;
+                                            const float b2 = (1.0f - b0) - b1;
+                                            float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
+                                            zw = zw + 0.0f;
+                                            if (zw >= -1.0f && zw <= 1.0f) resolve_sample(row + cc, zw, id);
+                                        }
+                                        e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
+                                    }
+                                    e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
+                                    row += W;
+                                }
+                            } else {
+                                push = (npix <= kMediumMaxPix) ? 1 : 2;
+                                entry = (uint32_t)(t + P.tri_base);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // warp-aggregated queue append: medium from the front, large / slow from the back
+#pragma unroll
+    for (int q = 1; q <= 2; ++q) {
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, push == q);
+        if (m == 0) continue;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(P.counters + 4 * b + (q - 1), __popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (push == q) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            uint32_t *qv = P.queue + (size_t)b * P.Fq;
+            if (q == 1) qv[slot] = entry;
+            else qv[P.Fq - 1 - slot] = entry;
+        }
+    }
+}
+
+// One warp rasterises one snapped triangle (or the stripe-th share of its 32x32 blocks).
+template <bool LARGE>
+__device__ void warp_raster(int x0, int y0, int x1, int y1, int x2, int y2, float z0, float z1, float z2,
+                            uint32_t id, int W, int H, unsigned long long *depth_view, int stripe, unsigned lane)
+{
+    long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+    if (area2 == 0) return;
+    if (area2 < 0) {
+        int ti; float tf;
+        ti = x1; x1 = x2; x2 = ti;
+        ti = y1; y1 = y2; y2 = ti;
+        tf = z1; z1 = z2; z2 = tf;
+        area2 = -area2;
+    }
+    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+    const int ox = 8 - 8 * W, oy = 8 - 8 * H;
+    const int c0 = max(ceil_div16(xmin - ox), 0), c1 = min(floor_div16(xmax - ox), W - 1);
+    const int r0 = max(ceil_div16(ymin - oy), 0), r1 = min(floor_div16(ymax - oy), H - 1);
+    if (c0 > c1 || r0 > r1) return;
+    const int dx0 = x2 - x1, dy0 = y2 - y1;
+    const int dx1 = x0 - x2, dy1 = y0 - y2;
+    const int dx2 = x1 - x0, dy2 = y1 - y0;
+    const long long bias0 = top_left(dx0, dy0) ? 0 : 1;
+    const long long bias1 = top_left(dx1, dy1) ? 0 : 1;
+    const long long bias2 = top_left(dx2, dy2) ? 0 : 1;
+    const float inv_area = 1.0f / __ll2float_rn(area2);
+    const int lx = lane & 7, ly = lane >> 3;
+
+    auto footprint = [&](int fx, int fy, int cl, int ch, int rl, int rh) {
+        const int cc = fx + lx, rr = fy + ly;
+        const int px = 16 * cc + ox, py = 16 * rr + oy;
+        const long long e0 = (long long)dx0 * (py - y1) - (long long)dy0 * (px - x1);
+        const long long e1 = (long long)dx1 * (py - y2) - (long long)dy1 * (px - x2);
+        const long long e2 = (long long)dx2 * (py - y0) - (long long)dy2 * (px - x0);
+        const bool cov = cc >= cl && cc <= ch && rr >= rl && rr <= rh && e0 >= bias0 && e1 >= bias1 && e2 >= bias2;
+        if (__ballot_sync(0xFFFFFFFFu, cov) == 0) return;
+        if (cov) {
+            const float b0 = __ll2float_rn(e0) * inv_area;
+            const float b1 = __ll2float_rn(e1) * inv_area;
+            const float b2 = (1.0f - b0) - b1;
+            float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
+            zw = zw + 0.0f;
+            if (zw >= -1.0f && zw <= 1.0f) resolve_sample(depth_view + (size_t)rr * W + cc, zw, id);
+        }
+    };
+
+    if (!LARGE) {
+        for (int fy = r0 & ~3; fy <= r1; fy += 4)
+            for (int fx = c0 & ~7; fx <= c1; fx += 8) footprint(fx, fy, c0, c1, r0, r1);
+    } else {
+        const int bx0 = c0 >> 5, bx1 = c1 >> 5, by0 = r0 >> 5, by1 = r1 >> 5;
+        const int nbx = bx1 - bx0 + 1;
+        const long long nblocks = (long long)nbx * (by1 - by0 + 1);
+        for (long long j = stripe; j < nblocks; j += kLargeStripes) {
+            const int bx = bx0 + (int)(j % nbx), by = by0 + (int)(j / nbx);
+            const int cl = max(c0, bx * 32), ch = min(c1, bx * 32 + 31);
+            const int rl = max(r0, by * 32), rh = min(r1, by * 32 + 31);
+            // conservative reject: evaluate every edge at the block corner where it is largest
+            const int pxl = 16 * cl + ox, pxh = 16 * ch + ox, pyl = 16 * rl + oy, pyh = 16 * rh + oy;
+            const long long m0 = (long long)dx0 * ((dx0 >= 0 ? pyh : pyl) - y1) - (long long)dy0 * ((dy0 >= 0 ? pxl : pxh) - x1);
+            const long long m1 = (long long)dx1 * ((dx1 >= 0 ? pyh : pyl) - y2) - (long long)dy1 * ((dy1 >= 0 ? pxl : pxh) - x2);
+            const long long m2 = (long long)dx2 * ((dx2 >= 0 ? pyh : pyl) - y0) - (long long)dy2 * ((dy2 >= 0 ? pxl : pxh) - x0);
+            if (m0 < bias0 || m1 < bias1 || m2 < bias2) continue;
+            for (int fy = rl & ~3; fy <= rh; fy += 4)
+                for (int fx = cl & ~7; fx <= ch; fx += 8) footprint(fx, fy, cl, ch, rl, rh);
+        }
+    }
+}
+
+__device__ __forceinline__ float plane_dist(int k, const float4 &p)
+{
+    switch (k) {
+    case 0: return p.z + p.w;
+    case 1: return p.w - p.z;
+    case 2: return p.x + WR_GUARD_BAND * p.w;
+    case 3: return WR_GUARD_BAND * p.w - p.x;
+    case 4: return p.y + WR_GUARD_BAND * p.w;
+    default: return WR_GUARD_BAND * p.w - p.y;
+    }
+}
+
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return (b - a) * t + a; }
+
+// Sutherland-Hodgman against near, far and the four guard-band planes, fixed order.
+// Executed by one lane; poly / tmp live in shared memory.
+__device__ int clip_polygon(float4 *poly, float4 *tmp, int n)
+{
+    float d[12];
+    for (int k = 0; k < 6; ++k) {
+        for (int i = 0; i < n; ++i) d[i] = plane_dist(k, poly[i]);
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const int j = (i + 1 == n) ? 0 : i + 1;
+            const bool in_i = d[i] >= 0.0f, in_j = d[j] >= 0.0f;
+            if (in_i) tmp[m++] = poly[i];
+            if (in_i != in_j) {
+                const float t = d[i] / (d[i] - d[j]);
+                float4 q;
+                q.x = lerp1(poly[i].x, poly[j].x, t);
+                q.y = lerp1(poly[i].y, poly[j].y, t);
+                q.z = lerp1(poly[i].z, poly[j].z, t);
+                q.w = lerp1(poly[i].w, poly[j].w, t);
+                tmp[m++] = q;
+            }
+        }
+        n = m;
+        if (n < 3) return 0;
+        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+    }
+    return n;
+}
+
+struct WarpClipScratch {
+    float4 poly[12];
+    float4 tmp[12];
+    int X[12], Y[12];
+    float zw[12];
+    int n;
+};
+
+template <bool LARGE>
+__global__ void __launch_bounds__(256) k_raster_queue(RasterParams P, VtxSrc src, int view0)
+{
+    __shared__ WarpClipScratch clip_smem[LARGE ? 8 : 1];
+    const int b = blockIdx.y + view0;
+    const unsigned lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long warps_total = (long long)gridDim.x * 8;
+    const long long gw = (long long)blockIdx.x * 8 + warp;
+    const int count = P.counters[4 * b + (LARGE ? 1 : 0)];
+    const uint32_t *qv = P.queue + (size_t)b * P.Fq;
+    unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
+    const long long items = LARGE ? (long long)count * kLargeStripes : (long long)count;
+
+    for (long long wi = gw; wi < items; wi += warps_total) {
+        const int qi = LARGE ? (int)(wi / kLargeStripes) : (int)wi;
+        const int stripe = LARGE ? (int)(wi % kLargeStripes) : 0;
+        const uint32_t entry = LARGE ? qv[P.Fq - 1 - qi] : qv[qi];
+        const uint32_t id = entry & ~WR_QUEUE_SLOW;
+        const int t = (int)id - P.tri_base;
+        const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
+                  i2 = __ldg(P.tri + 3 * (size_t)t + 2);
+        if (!(entry & WR_QUEUE_SLOW)) {
+            const size_t vb = (size_t)b * P.V;
+            const SnapVert a = load_sv(P.sv, vb + i0), c = load_sv(P.sv, vb + i1), d = load_sv(P.sv, vb + i2);
+            warp_raster<LARGE>(a.x, a.y, c.x, c.y, d.x, d.y, a.zw, c.zw, d.zw, id, P.W, P.H, depth_view, stripe, lane);
+        } else if (LARGE) {
+            WarpClipScratch &S = clip_smem[warp];
+            __syncwarp();
+            if (lane == 0) {
+                S.poly[0] = wr_load_clip(src, b, i0);
+                S.poly[1] = wr_load_clip(src, b, i1);
+                S.poly[2] = wr_load_clip(src, b, i2);
+                int n = clip_polygon(S.poly, S.tmp, 3);
+                for (int i = 0; i < n; ++i) {
+                    const float4 p = S.poly[i];
+                    bool ok = false;
+                    if (p.w > 0.0f) {
+                        const float rw = 1.0f / p.w;
+                        const float fx = (p.x * (float)(8 * P.W)) * rw;
+                        const float fy = (p.y * (float)(8 * P.H)) * rw;
+                        if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
+                            S.X[i] = __float2int_rn(fx);
+                            S.Y[i] = __float2int_rn(fy);
+                            S.zw[i] = p.z * rw;
+                            ok = true;
+                        }
+                    }
+                    if (!ok) { n = 0; break; }  // unrepresentable vertex: drop the whole polygon
+                }
+                S.n = n;
+            }
+            __syncwarp();
+            const int n = S.n;
+            for (int i = 1; i + 1 < n; ++i)  // fan (0, i, i+1); sub-triangles keep the parent id
+                warp_raster<LARGE>(S.X[0], S.Y[0], S.X[i], S.Y[i], S.X[i + 1], S.Y[i + 1], S.zw[0], S.zw[i],
+                                   S.zw[i + 1], id, P.W, P.H, depth_view, stripe, lane);
+        }
+    }
+}
+
+// (u, v, z/w) of the winning triangle at a pixel centre from the unsnapped clip-space vertices
+// (DESIGN.md 3.4).  Shared with the fused render kernel through common include below.
+__global__ void __launch_bounds__(256) k_resolve_rast(const unsigned long long *packed, VtxSrc src, const int32_t *tri,
+                                                      int H, int W, float *rast, int32_t *tri_id)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int b = blockIdx.z;
+    if (c >= W) return;
+    const size_t o = ((size_t)b * H + r) * W + c;
+    const unsigned long long pk = packed[o];
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    int id = -1;
+    if (pk != WR_EMPTY_PIXEL) {
+        id = (int)(uint32_t)(pk & 0xFFFFFFFFull);
+        const int i0 = __ldg(tri + 3 * (size_t)id), i1 = __ldg(tri + 3 * (size_t)id + 1), i2 = __ldg(tri + 3 * (size_t)id + 2);
+        const float4 p0 = wr_load_clip(src, b, i0), p1 = wr_load_clip(src, b, i1), p2 = wr_load_clip(src, b, i2);
+        const float fx = (float)(2 * c + 1 - W) / (float)W;
+        const float fy = (float)(2 * r + 1 - H) / (float)H;
+        const float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
+        const float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
+        const float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
+        const float a0 = p1x * p2y - p1y * p2x;
+        const float a1 = p2x * p0y - p2y * p0x;
+        const float a2 = p0x * p1y - p0y * p1x;
+        const float iw = 1.0f / ((a0 + a1) + a2);
+        const float b0 = a0 * iw, b1 = a1 * iw;
+        const float z = ((p0.z * a0) + (p1.z * a1)) + (p2.z * a2);
+        const float w = ((p0.w * a0) + (p1.w * a1)) + (p2.w * a2);
+        const float zw = z / w;
+        out.x = (b0 >= 0.0f) ? (b0 > 1.0f ? 1.0f : b0) : 0.0f;
+        out.y = (b1 >= 0.0f) ? (b1 > 1.0f ? 1.0f : b1) : 0.0f;
+        out.z = (zw >= -1.0f) ? (zw > 1.0f ? 1.0f : zw) : -1.0f;
+        out.w = (float)(id + 1);
+    }
+    if (rast) reinterpret_cast<float4 *>(rast)[o] = out;
+    if (tri_id) tri_id[o] = id;
+}
+
+}  // namespace
+
+// Runs snap -> setup -> queue rasterisation into the context scratch.  `extra_bytes` of additional
+// scratch are reserved behind the raster buffers and returned through `extra`.
+int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
+                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream)
+{
+    const int V = src.V;
+    const size_t sv_bytes = wr_align256((size_t)B * (size_t)(V > 0 ? V : 1) * sizeof(SnapVert));
+    const size_t depth_bytes = wr_align256((size_t)B * H * W * sizeof(unsigned long long));
+    const size_t queue_bytes = wr_align256((size_t)B * (size_t)(F > 0 ? F : 1) * sizeof(uint32_t));
+    const size_t stats_bytes = wr_align256((size_t)B * 8 * sizeof(int));
+    const size_t total = sv_bytes + depth_bytes + queue_bytes + stats_bytes + wr_align256(extra_bytes);
+    int rc = wr_scratch_reserve(ctx, total, stream);
+    if (rc != WR_OK) return rc;
+    char *base = static_cast<char *>(ctx->scratch);
+    SnapVert *sv = reinterpret_cast<SnapVert *>(base);
+    unsigned long long *depth = reinterpret_cast<unsigned long long *>(base + sv_bytes);
+    uint32_t *queue = reinterpret_cast<uint32_t *>(base + sv_bytes + depth_bytes);
+    int *stats = reinterpret_cast<int *>(base + sv_bytes + depth_bytes + queue_bytes);  // [B,4] counters + [B,4] user
+    if (extra) *extra = base + sv_bytes + depth_bytes + queue_bytes + stats_bytes;
+
+    cudaError_t e = cudaMemsetAsync(depth, 0xFF, (size_t)B * H * W * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset depth");
+    e = cudaMemsetAsync(stats, 0, (size_t)B * 8 * sizeof(int), stream);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset counters");
+    res->packed = depth;
+    res->view_stats = stats + 4 * B;
+
+    if (F > 0 && V > 0 && B > 0) {
+        RasterParams P;
+        P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
+        P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
+        const int qgrid = ctx->sm_count * 2;
+        k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv);
+        WR_CHECK_LAUNCH(ctx, "k_snap_vertices");
+        if (!tri_ranges) {
+            k_setup_triangles<<<dim3(wr_div_up(F, 256), B), 256, 0, stream>>>(P, 0);
+            WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
+            k_raster_queue<false><<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
+            WR_CHECK_LAUNCH(ctx, "k_raster_queue<medium>");
+            k_raster_queue<true><<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
+            WR_CHECK_LAUNCH(ctx, "k_raster_queue<large>");
+        } else {
+            for (int b = 0; b < B; ++b) {
+                const int start = tri_ranges[2 * b], count = tri_ranges[2 * b + 1];
+                if (start < 0 || count < 0 || (long long)start + count > F) return WR_ERR_INVALID_ARGUMENT;
+                if (count == 0) continue;
+                RasterParams Q = P;
+                Q.tri = tri + 3 * (size_t)start; Q.F = count; Q.tri_base = start;
+                k_setup_triangles<<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b);
+                WR_CHECK_LAUNCH(ctx, "k_setup_triangles(range)");
+                k_raster_queue<false><<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
+                WR_CHECK_LAUNCH(ctx, "k_raster_queue<medium>(range)");
+                k_raster_queue<true><<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
+                WR_CHECK_LAUNCH(ctx, "k_raster_queue<large>(range)");
+            }
+        }
+    }
+    return WR_OK;
+}
+
+extern "C" int wr_rasterize(wr_ctx *ctx, const float *pos, int B, int V, int pos_batched, const int32_t *tri, int F,
+                            const int32_t *tri_ranges, int H, int W, float *rast, int32_t *tri_id, void *stream_)
+{
+    if (!ctx || B < 0 || V < 0 || F < 0 || H <= 0 || W <= 0 || H > 8192 || W > 8192) return WR_ERR_INVALID_ARGUMENT;
+    if (F >= (1 << 30)) return WR_ERR_UNSUPPORTED;
+    if ((V > 0 && !pos) || (F > 0 && !tri)) return WR_ERR_INVALID_ARGUMENT;
+    if (B == 0) return WR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
+    VtxSrc src;
+    src.pos = pos; src.mvp = nullptr; src.V = V; src.batched = pos_batched ? 1 : 0;
+    RasterResult res;
+    int rc = wr_run_raster(ctx, src, B, tri, F, tri_ranges, H, W, 0, &res, nullptr, stream);
+    if (rc != WR_OK) return rc;
+    if (rast || tri_id) {
+        k_resolve_rast<<<dim3(wr_div_up(W, 256), H, B), 256, 0, stream>>>(res.packed, src, tri, H, W, rast, tri_id);
+        WR_CHECK_LAUNCH(ctx, "k_resolve_rast");
+    }
+    return WR_OK;
+}

@@ -1,0 +1,137 @@
+"""CameraProjection: bake view images into the mesh's UV atlas.
+
+Drop-in for mvadapter/utils/mesh_utils/projection.py of the reference (`CameraProjectionOutput`
+:33-38, `CameraProjection.__init__` :42-52, `__call__` :54-204).  The call keeps the reference's
+keyword surface; internally it is four launches groups on one stream:
+
+    uv_precompute        wr_rasterize + wr_interpolate in UV space              (uv.py:24-53)
+    view pass            wr_render (geometry, SimpleNormalization bg 1e2) + wr_view_prep
+    unprojection         wr_uv_unproject: per texel, all views, validity, weights, blend, stitch
+    (multi-GPU)          accumulators -> all_reduce(SUM) -> wr_uv_finalize      (parallel.py)
+
+Options outside the hot path raise NotImplementedError instead of silently doing something else:
+`poisson_blending=True`, `uv_padding=True`, `warp_images=True`, `remove_bg=True` without a remover.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .camera import Camera, get_camera
+from .mesh import TexturedMesh
+from .render import NVDiffRastContextWrapper
+from .utils import IMAGE_TYPE, LIST_TYPE, image_to_tensor
+from .uv import fused_unproject, fused_view_maps, uv_precompute
+
+
+@dataclass
+class CameraProjectionOutput:
+    uv_proj: torch.Tensor
+    uv_proj_mask: torch.Tensor
+    uv_depth_grad: Optional[torch.Tensor]
+    uv_aoi_cos: Optional[torch.Tensor]
+
+
+class CameraProjection:
+    def __init__(self, pb_backend: Optional[str] = None, bg_remover=None, device: str = "cuda",
+                 context_type: str = "gl") -> None:
+        # pb_backend selects the reference's Poisson solver backend (blend.py); Poisson blending is
+        # outside this package, the argument is accepted so constructor calls stay source compatible.
+        self.pb_backend = pb_backend
+        self.pb_solver = None
+        self.ctx = NVDiffRastContextWrapper(device, context_type)
+        self.bg_remover = bg_remover
+        self.device = device
+
+    def __call__(
+        self,
+        images: IMAGE_TYPE,
+        mesh: TexturedMesh,
+        cam: Optional[Camera] = None,
+        fovy_deg: Optional[LIST_TYPE] = None,
+        masks: Optional[IMAGE_TYPE] = None,
+        remove_bg: bool = False,
+        c2w: Optional[torch.Tensor] = None,
+        elevation_deg: Optional[LIST_TYPE] = None,
+        distance: Optional[LIST_TYPE] = None,
+        azimuth_deg: Optional[LIST_TYPE] = None,
+        num_views: Optional[int] = None,
+        uv_size: int = 2048,
+        warp_images: bool = False,
+        images_background: Optional[float] = None,
+        iou_rejection_threshold: Optional[float] = 0.8,
+        aoi_cos_valid_threshold: float = 0.3,
+        depth_grad_dilation: int = 5,
+        depth_grad_threshold: float = 0.1,
+        uv_exp_blend_alpha: float = 6,
+        uv_exp_blend_view_weight: Optional[torch.Tensor] = None,
+        poisson_blending: bool = True,
+        pb_num_iters: int = 1000,
+        pb_keep_original_border: bool = True,
+        from_scratch: bool = False,
+        uv_padding: bool = True,
+        return_uv_projection_mask: bool = False,
+        return_dict: bool = False,
+    ):
+        if poisson_blending:
+            raise NotImplementedError("poisson_blending=True needs the Poisson solver (reference blend.py), which is "
+                                      "outside the scope of worldrenderer_b200; pass poisson_blending=False")
+        if uv_padding:
+            raise NotImplementedError("uv_padding=True needs the seam inpainting of the reference (cvcuda, "
+                                      "cv_ops.py), which is outside the scope of worldrenderer_b200; pass "
+                                      "uv_padding=False")
+        if warp_images:
+            raise NotImplementedError("warp_images=True (reference warp.py) is outside the scope of worldrenderer_b200")
+
+        images_pt = image_to_tensor(images, device=self.device)
+        assert images_pt.ndim == 4
+        Nv, H, W, C = images_pt.shape
+        if C != 3:
+            raise ValueError(f"images must have 3 channels to be baked into the RGB atlas, got {C}")
+
+        if masks is not None:
+            masks_pt = image_to_tensor(masks, device=self.device)
+        elif remove_bg:
+            assert self.bg_remover is not None
+            masks_pt = self.bg_remover(images_pt)
+        else:
+            masks_pt = None
+        if masks_pt is not None and masks_pt.ndim == 4:
+            masks_pt = masks_pt.mean(-1)
+
+        if cam is None:
+            cam = get_camera(elevation_deg, distance, fovy_deg, azimuth_deg, num_views, c2w, aspect_wh=W / H,
+                             device=self.device)
+
+        pre = uv_precompute(self.ctx, mesh, height=uv_size, width=uv_size)
+        view_mask, geo_map, attr_map = fused_view_maps(self.ctx, mesh, cam, images_pt, H, W,
+                                                       int(depth_grad_dilation))
+
+        if masks_pt is not None and iou_rejection_threshold is not None:  # projection.py:125-138
+            given = (masks_pt > 0.5).float()
+            rendered = view_mask.float()
+            inter = given * rendered
+            union = given + rendered - inter
+            iou = inter.sum((1, 2)) / union.sum((1, 2))
+            iou_min = iou.min()
+            print(f"Debug: Per view IoU: {iou.tolist()}")
+            if iou_min < iou_rejection_threshold:
+                print(f"Warning: Minimum view IoU {iou_min} below threshold {iou_rejection_threshold}, "
+                      "skipping camera projection!")
+                return None
+
+        if masks_pt is None:
+            print("No view mask provided for UV blending, using all valid pixels")
+        blend, valid_any, _, uv_depth_grad, uv_aoi_cos = fused_unproject(
+            self.ctx, pre, cam, H, W, geo_map, attr_map, view_masks=masks_pt,
+            aoi_cos_thresh=aoi_cos_valid_threshold, depth_grad_thresh=depth_grad_threshold,
+            alpha=uv_exp_blend_alpha, view_weight=uv_exp_blend_view_weight, want_per_view=return_dict)
+
+        if return_dict:
+            return CameraProjectionOutput(uv_proj=blend, uv_proj_mask=valid_any, uv_depth_grad=uv_depth_grad,
+                                          uv_aoi_cos=uv_aoi_cos)
+        if return_uv_projection_mask:
+            return blend, valid_any
+        return blend
