@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the geometry path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config B of SURVEY.md section 8d, `configs[1]` of BASELINE.json): one synthetic 1M-face
+terrain mesh per GPU, the canonical 6-view orthographic rig, 768x768, outputs mask + position +
+view depth (DepthControlNetNormalization) + normal.  One STEP = one render() call = 6 views.
+With N GPUs every rank renders its own mesh (seed = rank) -- the by-mesh sharding of config D, no
+data-path collective -- so scaling is weak and `value` = N * 6 * K / (max over ranks of the timed time).
+
+JSON keys beyond the base contract:
+  roofline      dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
+  pipeline      whole render step against the same peak (12F + 24V + 33HW bytes per view)
+  stages        per-kernel ms (CUDA events recorded by the library on its launch stream)
+  cpu_baseline  the oracle port of the reference's render path timed on this box's host cores
+  e2e           same metric through the public API with host buffers (H2D of the mesh, D2H of the maps)
+  bake          ms per UV bake, config C (6 x 768^2 images -> 1024^2 atlas), device resident
+
+`--impl reference` times the reference's render path on the host cores.  The reference has no CPU
+implementation of its own (its rasterizer is the GPU-only nvdiffrast), so this arm is the oracle
+port: the reference's Python restated in NumPy over the C/OpenMP restatement of the operators.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 768
+N_VIEWS = 6
+TERRAIN = (1000, 500)  # quads -> 1 000 000 faces, 501 501 vertices
+METRIC = "views_per_sec_768sq_pos_normal_1M_face_mesh"
+UNIT = "views/s"
+
+
+def terrain_arrays(seed: int):
+    from worldrenderer_b200 import synth
+    v, f = synth.terrain(TERRAIN[0], TERRAIN[1], seed)
+    v = v / np.abs(v).max() * 0.5                       # load_mesh(rescale=True, scale=0.5)
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1)      # load_mesh axis remap (up=+y, front=+x)
+    return np.ascontiguousarray(v, np.float32), np.ascontiguousarray(f, np.int64)
+
+
+def algorithmic_bytes_per_view(F: int, V: int) -> dict:
+    """compulsory HBM traffic of one rendered view, split by the kernel that owns it."""
+    return {
+        "k_snap_vertices": 12 * V,                 # f32 positions read once
+        "k_setup_triangles": 12 * F,               # i32 indices read once
+        "k_shade4": 12 * V + 33 * H * W,           # f32 normals + per pixel 4 id + 4 depth + 12 pos + 12 normal + 1 mask
+        "k_shade": 12 * V + 33 * H * W,
+        "total": 12 * F + 24 * V + 33 * H * W,
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": int(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_render_setup(seed: int = 0):
+    import worldrenderer_b200 as wr
+    from oracle import render_oracle
+    from worldrenderer_b200 import synth
+    v, f = terrain_arrays(seed)
+    f32 = f.astype(np.int32)
+    cam = wr.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    v_nrm = render_oracle.vertex_normals(v, f32)  # once per mesh, outside the timed steps (as on the GPU arm's value)
+    return v, f32, v_nrm, cam.mvp_mtx.numpy(), cam.w2c.numpy()
+
+
+def cpu_render_step(state, views: int = N_VIEWS):
+    from oracle import render_oracle
+    v, f32, v_nrm, mvp, w2c = state
+    return render_oracle.render(v, f32, mvp[:views], w2c[:views], H, W, v_nrm=v_nrm)
+
+
+def cpu_threads() -> int:
+    from oracle import shim
+    return shim.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    state = cpu_render_setup(0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_render_step(state)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_render_step(state)
+    dt = time.perf_counter() - t0
+    value = N_VIEWS * args.steps / dt
+    cores = cpu_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, flush=False),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full steps (6 views 768^2 of the 1M-face mesh each), "
+                                   f"oracle/render_oracle.py over oracle/wr_oracle.c with {cores} OpenMP threads; "
+                                   "the reference itself has no CPU path (nvdiffrast is GPU-only)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int, flush: bool = True):
+    return {"workload": "config B: 1M-face procedural terrain (501501 vertices), canonical 6-view orthographic rig, "
+                        "768x768, outputs mask+position+depth(controlnet)+normal; one mesh per GPU (seed = rank)",
+            "faces": 2 * TERRAIN[0] * TERRAIN[1], "views_per_step": N_VIEWS, "resolution": [H, W],
+            "parallelism": f"by-mesh x{n_gpus}, no collective",
+            "l2": "flushed between timed steps by a 512 MiB device write outside the per-step events" if flush
+                  else "n/a (host run)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import worldrenderer_b200 as wr
+    from worldrenderer_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: worldrenderer_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    v_np, f_np = terrain_arrays(rank)
+    V, F = v_np.shape[0], f_np.shape[0]
+    ctx = wr.NVDiffRastContextWrapper(str(dev), "cuda")
+    cam = wr.get_orthogonal_camera(device=str(dev), **synth.CANONICAL_RIG)
+
+    def make_mesh(v_t, f_t):
+        m = wr.TexturedMesh(v_pos=v_t, t_pos_idx=f_t)
+        m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+        return m
+
+    mesh = make_mesh(torch.from_numpy(v_np).to(dev), torch.from_numpy(f_np).to(dev))
+    mesh.v_nrm  # vertex normals: once per mesh, like the reference's lazy property
+
+    def step():
+        return wr.render(ctx, mesh, cam, H, W, render_attr=False, render_depth=True, render_normal=True)
+
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        out = step()
+    barrier()
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps -------------------
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    sampler = ClockSampler(local)
+    barrier()
+    with sampler:
+        t_wall0 = time.perf_counter()
+        for k in range(K):
+            flush_buf.fill_(k & 0xFF)
+            starts[k].record()
+            out = step()
+            stops[k].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [starts[k].elapsed_time(stops[k]) for k in range(K)]
+    total_ms = float(sum(step_ms))
+    tot = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tot.item())
+    value = world * N_VIEWS * K / (total_ms_max * 1e-3)
+
+    # ---- per-kernel stage timing (same steps, library-side events), rank 0 ------------------------
+    stages, launches_per_step = {}, 0
+    if rank == 0:
+        ctx.ctx.profile(True)
+        reps = min(K, 20)
+        for k in range(reps):
+            flush_buf.fill_(k & 0xFF)
+            step()
+            for name, ms in ctx.ctx.profile_read():
+                stages.setdefault(name, []).append(ms)
+        ctx.ctx.profile(False)
+        launches_per_step = sum(1 for n in stages if n.startswith("k_"))
+        stages = {n: float(np.mean(ms)) for n, ms in stages.items()}
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public API with host buffers ---------------------------------------
+    v_host = torch.from_numpy(v_np).pin_memory()
+    f_host = torch.from_numpy(f_np).pin_memory()
+    mvp_host, w2c_host = cam.mvp_mtx.cpu().pin_memory(), cam.w2c.cpu().pin_memory()
+    host_out = {
+        "mask": torch.empty((N_VIEWS, H, W), dtype=torch.bool).pin_memory(),
+        "pos": torch.empty((N_VIEWS, H, W, 3), dtype=torch.float32).pin_memory(),
+        "depth": torch.empty((N_VIEWS, H, W), dtype=torch.float32).pin_memory(),
+        "normal": torch.empty((N_VIEWS, H, W, 3), dtype=torch.float32).pin_memory(),
+    }
+    h2d = v_host.numel() * 4 + f_host.numel() * 8 + 2 * mvp_host.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+
+    def e2e_step():
+        m = make_mesh(v_host.to(dev, non_blocking=True), f_host.to(dev, non_blocking=True))
+        c = wr.Camera(c2w=None, w2c=w2c_host.to(dev, non_blocking=True), proj_mtx=cam.proj_mtx,
+                      mvp_mtx=mvp_host.to(dev, non_blocking=True), cam_pos=None)
+        o = wr.render(ctx, m, c, H, W, render_attr=False, render_depth=True, render_normal=True)
+        for name, dst in host_out.items():
+            dst.copy_(getattr(o, name), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    Ke = min(K, 30)
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_VIEWS * Ke / float(e2e_dt.item())
+
+    # ---- bake (config C), rank 0 -----------------------------------------------------------------
+    bake = None
+    if rank == 0 and not args.no_bake:
+        bake = bench_bake(ctx, dev, flush_buf)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ab = algorithmic_bytes_per_view(F, V)
+        kernel_stages = {n: ms for n, ms in stages.items() if n.startswith("k_") and n in ab}
+        dom = max(kernel_stages, key=kernel_stages.get) if kernel_stages else None
+        roofline = None
+        if dom is not None:
+            achieved = ab[dom] * N_VIEWS / (kernel_stages[dom] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": ab[dom] * N_VIEWS, "kernel_ms": kernel_stages[dom],
+                        "share_of_step": kernel_stages[dom] / max(sum(stages.values()), 1e-9)}
+        ms_per_step = total_ms_max / K
+        pipe_achieved = ab["total"] * N_VIEWS / (ms_per_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "roofline": roofline,
+            "pipeline": {"bound": "hbm", "achieved": pipe_achieved, "peak": peak, "unit": "GB/s",
+                         "frac": pipe_achieved / peak, "algorithmic_bytes_per_step": ab["total"] * N_VIEWS},
+            "stages_ms": stages,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "what": "render() per step on a mesh uploaded from pinned host memory (positions f32 + "
+                                         "faces i64 + cameras), vertex normals, 6 views, all four maps copied back to "
+                                         "pinned host memory"},
+            "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": t_wall,
+            "bake": bake,
+        }
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = bench_cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_cpu_baseline():
+    state = cpu_render_setup(0)
+    cpu_render_step(state)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 30):
+        cpu_render_step(state)
+        reps += 1
+    dt = time.perf_counter() - t0
+    cores = cpu_threads()
+    return {"value": N_VIEWS * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} full steps (6 views 768^2, same 1M-face mesh), oracle port of render.py:220-286 "
+                      f"with {cores} OpenMP threads; vertex normals excluded on both sides",
+            "ms_per_step": 1e3 * dt / reps}
+
+
+def bench_bake(ctx, dev, flush_buf):
+    """Config C: icosphere 50k faces with a cell atlas, 6 synthetic 768^2 images -> 1024^2 atlas."""
+    import torch
+
+    import worldrenderer_b200 as wr
+    from worldrenderer_b200 import synth
+    from worldrenderer_b200.uv import fused_unproject, fused_view_maps
+
+    v, f = synth.icosphere(50, 0.5)
+    vt, ft = synth.cell_atlas_uv(f.shape[0])
+    uv = 1024
+    mesh = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f, dtype=torch.int64),
+                           v_tex=torch.tensor(vt, dtype=torch.float32), t_tex_idx=torch.tensor(ft, dtype=torch.int64),
+                           texture=torch.zeros((uv, uv, 3), dtype=torch.float32))
+    mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
+    mesh.to(dev)
+    mesh.v_nrm
+    cam = wr.get_orthogonal_camera(device=str(dev), **synth.CANONICAL_RIG)
+    images = torch.from_numpy(synth.view_images(N_VIEWS, H, W, seed=1)).to(dev)
+    proj = wr.CameraProjection(None, None, str(dev), "cuda")
+    proj.ctx = ctx
+    kw = dict(uv_size=uv, poisson_blending=False, uv_padding=False, depth_grad_dilation=5, uv_exp_blend_alpha=3,
+              uv_exp_blend_view_weight=torch.ones(N_VIEWS), aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
+              iou_rejection_threshold=None, return_dict=True)
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        ms = []
+        for k in range(reps):
+            flush_buf.fill_(k & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.median(ms))
+
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # the call prints the reference's "No view mask" notice
+        e2e_ms = timed(lambda: proj(images, mesh, cam, **kw))
+        pre = wr.uv_precompute(ctx, mesh, uv, uv)
+        _, geo, att = fused_view_maps(ctx, mesh, cam, images, H, W, 5)
+        unproj_ms = timed(lambda: fused_unproject(ctx, pre, cam, H, W, geo, att, aoi_cos_thresh=0.2,
+                                                  depth_grad_thresh=0.1, alpha=3.0,
+                                                  view_weight=torch.ones(N_VIEWS, device=dev)))
+    peak, _ = peaks()
+    bytes_unproj = 32 * N_VIEWS * H * W + 38 * uv * uv
+    return {"workload": "config C: 50k-face icosphere, 6 x 768^2 images -> 1024^2 atlas, validity + cosine^3 weights",
+            "ms_per_uv_bake_end_to_end": e2e_ms, "ms_unprojection_only": unproj_ms,
+            "unprojection_algorithmic_bytes": bytes_unproj,
+            "unprojection_frac_of_hbm_peak": bytes_unproj / (unproj_ms * 1e-3) / 1e9 / peak}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bake", action="store_true", help="skip the config C bake timing")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40  # each step is ~0.1-1 s of host work; keep the arm within minutes
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

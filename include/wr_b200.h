@@ -63,6 +63,15 @@ void wr_ctx_destroy(wr_ctx *ctx);
 uint64_t wr_ctx_scratch_bytes(const wr_ctx *ctx);
 
 /*
+ * Measurement aid (no reference counterpart): with profiling enabled every entry point records a
+ * CUDA event on its launch stream before each of its kernels.  wr_ctx_profile_read waits for the last
+ * call's final event and returns the number of stages of that call, writing their durations (ms).
+ */
+int wr_ctx_profile(wr_ctx *ctx, int enable);
+int wr_ctx_profile_read(wr_ctx *ctx, float *stage_ms, int capacity);
+const char *wr_ctx_profile_stage_name(const wr_ctx *ctx, int i);
+
+/*
  * dr.rasterize.  pos: [B,V,4] f32 clip space when pos_batched != 0 (instanced mode), else [V,4]
  * shared by all B views.  tri: [F,3] i32.  tri_ranges: NULL, or HOST int32 [B,2] (start, count)
  * into tri (range mode; ids stay indices into tri).  rast: [B,H,W,4] f32 = (u, v, z/w, id+1),

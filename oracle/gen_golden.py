@@ -1,0 +1,193 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference Python on CPU.  TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):   python -m oracle.gen_golden
+
+The reference's render.py / uv.py / projection.py / camera.py / mesh.py execute as they are; only the
+absent `nvdiffrast.torch` operators are served by the C oracle (oracle/ref_shim.py).  The fixtures
+pin (a) the host-side API (cameras, load_mesh) of worldrenderer_b200 and (b) the NumPy restatement
+oracle/render_oracle.py, which is what the GPU box compares the CUDA kernels with.
+
+Inputs are stored next to the outputs so the tests never need the reference tree.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from worldrenderer_b200 import synth  # noqa: E402
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def cameras(mu):
+    rig = synth.CANONICAL_RIG
+    o = mu.get_orthogonal_camera(**rig)
+    p = mu.get_camera(elevation_deg=[10.0, -20.0, 35.0, 60.0], distance=[1.8] * 4, fovy_deg=[40.0] * 4,
+                      azimuth_deg=[0.0, 75.0, 160.0, 250.0], aspect_wh=4 / 3, near=0.05, far=20.0)
+    q = mu.get_camera(elevation_deg=[0.0] * 3, distance=[2.0] * 3, fovy_deg=[50.0] * 3, azimuth_deg=None, num_views=3)
+    frames = json.load(open(os.path.join(ref_shim.REFERENCE_ROOT, "mvadapter", "test", "camera_path.json")))
+    sel = [frames[i] for i in (0, 33, 66, 99)]
+    c2w = torch.tensor([f["matrix_world"] for f in sel], dtype=torch.float32)  # uniform scale 0.6 in the rotation
+    fov = torch.tensor([f["fov_deg"] for f in sel], dtype=torch.float32)
+    j = mu.get_camera(c2w=c2w, fovy_deg=fov, aspect_wh=720 / 480)
+    out = {"json_c2w": _np(c2w), "json_fov": _np(fov)}
+    for name, cam in (("ortho", o), ("persp", p), ("ring", q), ("json", j)):
+        for fld in ("c2w", "w2c", "proj_mtx", "mvp_mtx", "cam_pos"):
+            out[f"{name}_{fld}"] = _np(getattr(cam, fld))
+    w = torch.linalg.inv(p.c2w)
+    k = mu.get_camera(w2c=w, proj_mtx=p.proj_mtx)
+    out["w2conly_mvp_mtx"] = _np(k.mvp_mtx)
+    np.savez_compressed(os.path.join(OUT, "cameras.npz"), **out)
+
+
+def load_mesh_cases(mu):
+    rng = np.random.default_rng(3)
+    v, f = synth.icosphere(2, 1.0)
+    v = v * np.array([1.5, 0.7, 1.1]) + np.array([0.3, -0.2, 0.1]) + rng.normal(0, 0.01, v.shape)
+    out = {"vertices": v, "faces": f}
+    combos = {
+        "default": {},
+        "rescale": dict(rescale=True),
+        "center_rescale": dict(rescale=True, move_to_center=True, scale=0.45),
+        "zup": dict(shape_init_mesh_up="+z", shape_init_mesh_front="-y", rescale=True),
+        "x2y": dict(front_x_to_y=True, rescale=True),
+    }
+    with tempfile.TemporaryDirectory() as d:
+        path = synth.save_npz(os.path.join(d, "m.npz"), v, f)
+        for name, kw in combos.items():
+            m, off, sc = mu.load_mesh(path, return_transform=True, **kw)
+            out[f"{name}_v_pos"] = _np(m.v_pos)
+            out[f"{name}_t_pos_idx"] = _np(m.t_pos_idx)
+            out[f"{name}_offset"] = np.zeros(0) if off is None else np.asarray(off)
+            out[f"{name}_scale"] = np.zeros(0) if sc is None else np.asarray(sc)
+            out[f"{name}_v_nrm"] = _np(m.v_nrm)
+    np.savez_compressed(os.path.join(OUT, "load_mesh.npz"), **out)
+
+
+def _sphere_mesh(mu, freq, tex_size, seed=0):
+    v, f = synth.icosphere(freq, 0.5)
+    vt, ft = synth.cell_atlas_uv(f.shape[0])
+    rng = np.random.default_rng(seed)
+    tex = rng.uniform(0, 1, (tex_size, tex_size, 3)).astype(np.float32)
+    m = mu.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f, dtype=torch.int64),
+                        v_tex=torch.tensor(vt, dtype=torch.float32), t_tex_idx=torch.tensor(ft, dtype=torch.int64),
+                        texture=torch.tensor(tex))
+    m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+    return m
+
+
+def _terrain_mesh(mu, nx, ny):
+    v, f = synth.terrain(nx, ny, 0)
+    v = v / np.abs(v).max() * 0.5
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1)
+    m = mu.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f, dtype=torch.int64))
+    m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+    return m
+
+
+def _mesh_inputs(m):
+    d = {"v_pos": _np(m.v_pos), "t_pos_idx": _np(m.t_pos_idx).astype(np.int32)}
+    if m.v_tex is not None:
+        d.update(v_tex=_np(m.v_tex), t_tex_idx=_np(m.t_tex_idx).astype(np.int32), texture=_np(m.texture))
+    return d
+
+
+def render_cases(mu):
+    ctx = mu.NVDiffRastContextWrapper("cpu", "cuda")
+    m = _sphere_mesh(mu, 6, 16)
+    cam = mu.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    out = _mesh_inputs(m)
+    out.update(mvp=_np(cam.mvp_mtx), w2c=_np(cam.w2c), v_nrm=_np(m.v_nrm))
+    H = W = 64
+    r = mu.render(ctx, m, cam, H, W, render_attr=True, attr_background=0.25)
+    out.update(mask=_np(r.mask), pos=_np(r.pos), normal=_np(r.normal), depth_controlnet=_np(r.depth), attr_linear=_np(r.attr))
+    r = mu.render(ctx, m, cam, H, W, render_attr=True, texture_filter_mode="nearest",
+                  depth_normalization_strategy=mu.Zero123PlusPlusNormalization())
+    out.update(depth_zero123pp=_np(r.depth), attr_nearest=_np(r.attr))
+    r = mu.render(ctx, m, cam, H, W, render_attr=False, depth_normalization_strategy=mu.SimpleNormalization())
+    out.update(depth_simple=_np(r.depth))
+    r = mu.render(ctx, m, cam, H, W, render_attr=False, depth_normalization_strategy=None, normal_background=0.5)
+    out.update(depth_none=_np(r.depth), normal_bg05=_np(r.normal))
+    np.savez_compressed(os.path.join(OUT, "render_sphere.npz"), **out)
+
+    m = _terrain_mesh(mu, 32, 16)
+    cams = {
+        "persp": mu.get_camera(elevation_deg=[10.0, -20.0, 35.0, 60.0], distance=[1.8] * 4, fovy_deg=[40.0] * 4,
+                               azimuth_deg=[0.0, 75.0, 160.0, 250.0], aspect_wh=64 / 48),
+        "inside": mu.get_camera(elevation_deg=[5.0, 40.0], distance=[0.3, 0.45], fovy_deg=[70.0, 90.0],
+                                azimuth_deg=[20.0, 200.0], near=0.05, far=10.0, aspect_wh=64 / 48),
+    }
+    out = _mesh_inputs(m)
+    out["v_nrm"] = _np(m.v_nrm)
+    for name, cam in cams.items():
+        r = mu.render(ctx, m, cam, 48, 64, render_attr=False)
+        out.update({f"{name}_mvp": _np(cam.mvp_mtx), f"{name}_w2c": _np(cam.w2c), f"{name}_mask": _np(r.mask),
+                    f"{name}_pos": _np(r.pos), f"{name}_normal": _np(r.normal), f"{name}_depth": _np(r.depth)})
+    np.savez_compressed(os.path.join(OUT, "render_terrain.npz"), **out)
+
+
+def bake_cases(mu):
+    m = _sphere_mesh(mu, 6, 64, seed=2)
+    cam = mu.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    images = synth.view_images(6, 48, 48, seed=1)
+    proj = mu.CameraProjection(pb_backend="torch-native", bg_remover=None, device="cpu", context_type="cuda")
+    out = _mesh_inputs(m)
+    out.update(mvp=_np(cam.mvp_mtx), w2c=_np(cam.w2c), v_nrm=_np(m.v_nrm), images=images)
+    vw = torch.tensor([1.0, 0.5, 1.0, 2.0, 1.0, 1.0])
+    out["view_weight"] = _np(vw)
+    variants = {
+        "a": dict(aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1, uv_exp_blend_alpha=3.0,
+                  uv_exp_blend_view_weight=vw, depth_grad_dilation=5),
+        "b": dict(aoi_cos_valid_threshold=-1.0, depth_grad_threshold=None, uv_exp_blend_alpha=3.0,
+                  uv_exp_blend_view_weight=torch.ones(6), depth_grad_dilation=5),
+        "c": dict(aoi_cos_valid_threshold=0.3, depth_grad_threshold=0.1, uv_exp_blend_alpha=6.0, depth_grad_dilation=3),
+    }
+    for name, kw in variants.items():
+        r = proj(torch.from_numpy(images), m, cam, uv_size=64, poisson_blending=False, uv_padding=False,
+                 iou_rejection_threshold=None, return_dict=True, **kw)
+        out.update({f"{name}_uv_proj": _np(r.uv_proj), f"{name}_uv_proj_mask": _np(r.uv_proj_mask),
+                    f"{name}_uv_depth_grad": _np(r.uv_depth_grad), f"{name}_uv_aoi_cos": _np(r.uv_aoi_cos)})
+    # with view masks (the rendered masks themselves) -> exercises uv_mask_proj and the IoU branch
+    ctx = proj.ctx
+    masks = mu.render(ctx, m, cam, 48, 48, render_attr=False).mask.float()
+    r = proj(torch.from_numpy(images), m, cam, masks=masks, uv_size=64, poisson_blending=False, uv_padding=False,
+             return_dict=True)
+    out.update(masks=_np(masks), m_uv_proj=_np(r.uv_proj), m_uv_proj_mask=_np(r.uv_proj_mask))
+    # step-by-step intermediates for one configuration
+    pre = mu.uv.uv_precompute(ctx, m, 64, 64)
+    geo = mu.uv.uv_render_geometry(ctx, m, cam, 48, 48, pre, compute_depth_grad=True, depth_grad_dilation=5)
+    out.update(uv_mask=_np(pre.uv_mask), uv_pos=_np(pre.uv_pos), uv_pos_ndc=_np(geo.uv_pos_ndc),
+               uv_pos_error=_np(geo.uv_pos_error), view_aoi_cos=_np(geo.view_aoi_cos),
+               view_depth_grad=_np(geo.view_depth_grad)[:, 0], view_depth=_np(geo.view_depth))
+    np.savez_compressed(os.path.join(OUT, "bake_sphere.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    mu = ref_shim.load_reference()
+    import importlib
+    mu.uv = importlib.import_module("mvadapter.utils.mesh_utils.uv")
+    cameras(mu)
+    load_mesh_cases(mu)
+    render_cases(mu)
+    bake_cases(mu)
+    for n in sorted(os.listdir(OUT)):
+        print(n, os.path.getsize(os.path.join(OUT, n)))
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ _LIB: Optional[ctypes.CDLL] = None
 # every symbol include/wr_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "wr_status_string", "wr_ctx_last_error", "wr_version", "wr_ctx_create", "wr_ctx_destroy",
-    "wr_ctx_scratch_bytes", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
+    "wr_ctx_scratch_bytes", "wr_ctx_profile", "wr_ctx_profile_read", "wr_ctx_profile_stage_name", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
     "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample",
 ]
 
@@ -85,6 +85,12 @@ def lib() -> ctypes.CDLL:
     L.wr_ctx_destroy.argtypes = [vp]
     L.wr_ctx_scratch_bytes.restype = ctypes.c_uint64
     L.wr_ctx_scratch_bytes.argtypes = [vp]
+    L.wr_ctx_profile.restype = ci
+    L.wr_ctx_profile.argtypes = [vp, ci]
+    L.wr_ctx_profile_read.restype = ci
+    L.wr_ctx_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ci]
+    L.wr_ctx_profile_stage_name.restype = ctypes.c_char_p
+    L.wr_ctx_profile_stage_name.argtypes = [vp, ci]
     L.wr_rasterize.restype = ci
     L.wr_rasterize.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, ci, ci, vp, vp, vp]
     L.wr_interpolate.restype = ci
@@ -163,3 +169,15 @@ class NativeContext:
 
     def scratch_bytes(self) -> int:
         return int(self._lib.wr_ctx_scratch_bytes(self._h))
+
+    def profile(self, enable: bool) -> None:
+        """Per-kernel CUDA-event timing of the following calls (measurement aid for bench.py)."""
+        self.check(self._lib.wr_ctx_profile(self._h, int(bool(enable))), "wr_ctx_profile")
+
+    def profile_read(self):
+        """[(stage name, ms)] of the most recent native call; waits for it to finish."""
+        buf = (ctypes.c_float * 17)()
+        n = self._lib.wr_ctx_profile_read(self._h, buf, 17)
+        if n < 0:
+            self.check(n, "wr_ctx_profile_read")
+        return [(self._lib.wr_ctx_profile_stage_name(self._h, i).decode(), float(buf[i])) for i in range(n)]

@@ -44,13 +44,53 @@ extern "C" int wr_ctx_create(int device, wr_ctx **out)
     if (!ctx) return WR_ERR_OUT_OF_MEMORY;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    const char *tune = getenv("WR_TUNE");
+    ctx->tune = tune ? atoi(tune) : 0;
     *out = ctx;
     return WR_OK;
+}
+
+extern "C" int wr_ctx_profile(wr_ctx *ctx, int enable)
+{
+    if (!ctx) return WR_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    if (enable && !ctx->marks[0]) {
+        for (int i = 0; i <= WR_MAX_STAGES; ++i) {
+            cudaError_t e = cudaEventCreate(&ctx->marks[i]);
+            if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaEventCreate");
+        }
+    }
+    ctx->profiling = enable ? 1 : 0;
+    ctx->n_marks = 0;
+    return WR_OK;
+}
+
+extern "C" int wr_ctx_profile_read(wr_ctx *ctx, float *stage_ms, int capacity)
+{
+    if (!ctx || !ctx->profiling || ctx->n_marks < 2) return 0;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaEventSynchronize(ctx->marks[ctx->n_marks - 1]);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaEventSynchronize");
+    const int n = ctx->n_marks - 1;
+    for (int i = 0; i < n && i < capacity; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->marks[i], ctx->marks[i + 1]);
+        stage_ms[i] = ms;
+    }
+    return n;
+}
+
+extern "C" const char *wr_ctx_profile_stage_name(const wr_ctx *ctx, int i)
+{
+    if (!ctx || i < 0 || i >= ctx->n_marks) return "";
+    return ctx->mark_names[i];
 }
 
 extern "C" void wr_ctx_destroy(wr_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->marks[0])
+        for (int i = 0; i <= WR_MAX_STAGES; ++i) cudaEventDestroy(ctx->marks[i]);
     if (ctx->scratch) {
         cudaSetDevice(ctx->device);
         cudaFree(ctx->scratch);
@@ -63,6 +103,7 @@ int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream)
 {
     (void)stream;
     if (bytes <= ctx->scratch_bytes) return WR_OK;
+    ctx->clean_bytes = 0;
     if (ctx->scratch) {
         cudaFree(ctx->scratch);
         ctx->scratch = nullptr;

@@ -317,19 +317,24 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     if (need) {
         int rc = wr_scratch_reserve(ctx, need, stream);
         if (rc != WR_OK) return rc;
+        ctx->clean_bytes = 0;  // the temporaries overwrite the raster's packed buffer
         char *p = static_cast<char *>(ctx->scratch);
         if (!aoi_buf) { aoi_buf = reinterpret_cast<float *>(p); p += wr_align256(n * sizeof(float)); }
         if (dilation > 0) g_buf = reinterpret_cast<float *>(p);
     }
     const dim3 grid(wr_div_up(W, 256), H, B);
     // dilation 1 is the identity max-pool: write the gradient straight through the second kernel as well
+    wr_stage_begin(ctx);
+    wr_stage(ctx, stream, "k_view_aoi_sobel");
     k_view_aoi_sobel<<<grid, 256, 0, stream>>>(normal, mask, depth, w2c, H, W, dilation > 0, aoi_buf, g_buf);
     WR_CHECK_LAUNCH(ctx, "k_view_aoi_sobel");
     if (depth_grad || geo_map || attr_map) {
+        wr_stage(ctx, stream, "k_dilate_pack");
         k_dilate_pack<<<grid, 256, 0, stream>>>(aoi_buf, g_buf, position, images, H, W, dilation, depth_grad, geo_map,
                                                attr_map);
         WR_CHECK_LAUNCH(ctx, "k_dilate_pack");
     }
+    wr_stage(ctx, stream, "end");
     return WR_OK;
 }
 
@@ -348,8 +353,11 @@ extern "C" int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void 
     const int materialise = (A.uv_pos_ndc || A.uv_pos_proj || A.uv_pos_error || A.uv_aoi_cos || A.uv_depth_grad ||
                              A.uv_attr_proj || A.uv_mask_proj || A.uv_valid || A.uv_weight) ? 1 : 0;
     const long long ntex = (long long)A.Hu * A.Wu;
+    wr_stage_begin(ctx);
+    wr_stage(ctx, stream, "k_uv_unproject");
     k_uv_unproject<<<wr_div_up(ntex, 256), 256, smem, stream>>>(A, materialise);
     WR_CHECK_LAUNCH(ctx, "k_uv_unproject");
+    wr_stage(ctx, stream, "end");
     return WR_OK;
 }
 

@@ -66,19 +66,43 @@ __device__ __forceinline__ float wr_ordered_float(uint32_t k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+#define WR_MAX_STAGES 16
+
 struct wr_ctx {
     int device;
     int sm_count;
     void *scratch;
     size_t scratch_bytes;
     char last_error[256];
+    size_t clean_bytes;  // leading bytes of scratch (the packed depth/id buffer) known to be all 0xFF
+    int tune;  // experiment switches (env WR_TUNE), see csrc/raster.cu
+    // optional per-stage timing (bench.py): events recorded on the launch stream between kernels
+    int profiling;
+    int n_marks;
+    cudaEvent_t marks[WR_MAX_STAGES + 1];
+    const char *mark_names[WR_MAX_STAGES + 1];
 };
+
+// Marks the START of stage `name` (and the end of the previous one) on `stream` when profiling is on.
+static inline void wr_stage(wr_ctx *ctx, cudaStream_t stream, const char *name)
+{
+    if (!ctx->profiling || ctx->n_marks > WR_MAX_STAGES) return;
+    ctx->mark_names[ctx->n_marks] = name;
+    cudaEventRecord(ctx->marks[ctx->n_marks], stream);
+    ctx->n_marks++;
+}
+static inline void wr_stage_begin(wr_ctx *ctx) { ctx->n_marks = 0; }
 
 // result of the coverage / visibility stages: packed (depth_key << 32 | triangle id) per pixel
 struct RasterResult {
-    const unsigned long long *packed;  // [B,H,W]
-    int32_t *view_stats;               // [B,4] zero-initialised ints the caller may use
+    unsigned long long *packed;  // [B,H,W]
+    size_t packed_bytes;
+    int32_t *view_stats;         // [B,4] zero-initialised ints the caller may use
 };
+
+// The kernel that reads `packed` resets every pixel it consumes to WR_EMPTY_PIXEL; after its launch the
+// buffer is known clean again and the next call can skip the clear.
+static inline void wr_raster_consumed(wr_ctx *ctx, const RasterResult *res) { ctx->clean_bytes = res->packed_bytes; }
 
 int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream);
 int wr_set_cuda_error(wr_ctx *ctx, cudaError_t e, const char *where);

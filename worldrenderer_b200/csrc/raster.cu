@@ -84,6 +84,55 @@ __device__ __forceinline__ void resolve_sample(unsigned long long *dst, float zw
     atomicMin(dst, packed);
 }
 
+// Small triangle (pixel bbox <= kSmallMaxPix, snapped extent < kSmallMaxExtent): exact int32 edge
+// functions, one 64-bit atomicMin per covered sample.  DESIGN.md 3.3.
+__device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int x2, int y2, float z0, float z1,
+                                             float z2, uint32_t id, int c0, int c1, int r0, int r1, int W, int H,
+                                             unsigned long long *depth_view)
+{
+    int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);  // |extent| < 2^10: fits int32
+    if (area2 < 0) {
+        int ti; float tf;
+        ti = x1; x1 = x2; x2 = ti;
+        ti = y1; y1 = y2; y2 = ti;
+        tf = z1; z1 = z2; z2 = tf;
+        area2 = -area2;
+    }
+    const int dx0 = x2 - x1, dy0 = y2 - y1;  // edge opposite vertex 0
+    const int dx1 = x0 - x2, dy1 = y0 - y2;
+    const int dx2 = x1 - x0, dy2 = y1 - y0;
+    const int bias0 = top_left(dx0, dy0) ? 0 : 1;
+    const int bias1 = top_left(dx1, dy1) ? 0 : 1;
+    const int bias2 = top_left(dx2, dy2) ? 0 : 1;
+    const float inv_area = 1.0f / __int2float_rn(area2);
+    const int px0 = 16 * c0 + (8 - 8 * W), py0 = 16 * r0 + (8 - 8 * H);
+    int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
+    int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
+    int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
+    unsigned long long *row = depth_view + (size_t)r0 * W;
+#pragma unroll 1
+    for (int r = r0; r <= r1; ++r) {
+        int e0 = e0r, e1 = e1r, e2 = e2r;
+#pragma unroll 1
+        for (int cc = c0; cc <= c1; ++cc) {
+            if (e0 >= bias0 && e1 >= bias1 && e2 >= bias2) {
+                const float b0 = __int2float_rn(e0) * inv_area;
+                const float b1 = __int2float_rn(e1) * inv_area;
+                const float b2 = (1.0f - b0) - b1;
+                float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
+                zw = zw + 0.0f;
+                if (zw >= -1.0f && zw <= 1.0f) resolve_sample(row + cc, zw, id);
+            }
+            e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
+        }
+        e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
+        row += W;
+    }
+}
+
+// (A variant that compacted the block's live triangles through shared memory before the raster loop was
+// measured 29% SLOWER on config B -- 73.7 vs 57.3 us -- the kernel is bound by its dependent gathers,
+// not by divergence; see profiles/README.md.)
 __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,6 +141,9 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
     const unsigned lane = threadIdx.x & 31;
     int push = 0;  // 0 none, 1 medium, 2 large
     uint32_t entry = 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x2 = 0, y2 = 0, c0 = 0, c1 = 0, r0 = 0, r1 = 0;
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+    unsigned long long *depth_view = P.depth + (size_t)b * H * W;
 
     if (t < P.F) {
         const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
@@ -105,56 +157,20 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
                     push = 2;
                     entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
                 } else {
-                    int x0 = a.x, y0 = a.y, x1 = c.x, y1 = c.y, x2 = d.x, y2 = d.y;
-                    float z0 = a.zw, z1 = c.zw, z2 = d.zw;
-                    long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
-                    if (area2 != 0) {
-                        const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
-                        const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
-                        const int ox = 8 - 8 * W, oy = 8 - 8 * H;
-                        const int c0 = max(ceil_div16(xmin - ox), 0), c1 = min(floor_div16(xmax - ox), W - 1);
-                        const int r0 = max(ceil_div16(ymin - oy), 0), r1 = min(floor_div16(ymax - oy), H - 1);
-                        if (c0 <= c1 && r0 <= r1) {
+                    x0 = a.x; y0 = a.y; x1 = c.x; y1 = c.y; x2 = d.x; y2 = d.y;
+                    z0 = a.zw; z1 = c.zw; z2 = d.zw;
+                    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+                    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+                    const int ox = 8 - 8 * W, oy = 8 - 8 * H;
+                    c0 = max(ceil_div16(xmin - ox), 0); c1 = min(floor_div16(xmax - ox), W - 1);
+                    r0 = max(ceil_div16(ymin - oy), 0); r1 = min(floor_div16(ymax - oy), H - 1);
+                    if (c0 <= c1 && r0 <= r1) {
+                        const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+                        if (area2 != 0) {
                             const long long npix = (long long)(c1 - c0 + 1) * (r1 - r0 + 1);
-                            if (npix <= kSmallMaxPix && xmax - xmin < kSmallMaxExtent &&
-                                ymax - ymin < kSmallMaxExtent) {
-                                // ---- small triangle: rasterise here, int32 edge functions ----
-                                if (area2 < 0) {
-                                    int ti; float tf;
-                                    ti = x1; x1 = x2; x2 = ti;
-                                    ti = y1; y1 = y2; y2 = ti;
-                                    tf = z1; z1 = z2; z2 = tf;
-                                    area2 = -area2;
-                                }
-                                const int dx0 = x2 - x1, dy0 = y2 - y1;  // edge opposite vertex 0
-                                const int dx1 = x0 - x2, dy1 = y0 - y2;
-                                const int dx2 = x1 - x0, dy2 = y1 - y0;
-                                const int bias0 = top_left(dx0, dy0) ? 0 : 1;
-                                const int bias1 = top_left(dx1, dy1) ? 0 : 1;
-                                const int bias2 = top_left(dx2, dy2) ? 0 : 1;
-                                const float inv_area = 1.0f / __ll2float_rn(area2);
-                                const int px0 = 16 * c0 + ox, py0 = 16 * r0 + oy;
-                                int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
-                                int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
-                                int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
-                                unsigned long long *row = P.depth + ((size_t)b * H + r0) * W;
-                                const uint32_t id = (uint32_t)(t + P.tri_base);
-                                for (int r = r0; r <= r1; ++r) {
-                                    int e0 = e0r, e1 = e1r, e2 = e2r;
-                                    for (int cc = c0; cc <= c1; ++cc) {
-                                        if (e0 >= bias0 && e1 >= bias1 && e2 >= bias2) {
-                                            const float b0 = __int2float_rn(e0) * inv_area;
-                                            const float b1 = __int2float_rn(e1) * inv_area;
-                                            const float b2 = (1.0f - b0) - b1;
-                                            float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
-                                            zw = zw + 0.0f;
-                                            if (zw >= -1.0f && zw <= 1.0f) resolve_sample(row + cc, zw, id);
-                                        }
-                                        e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
-                                    }
-                                    e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
-                                    row += W;
-                                }
+                            if (npix <= kSmallMaxPix && xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
+                                raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0, c1,
+                                                  r0, r1, W, H, depth_view);
                             } else {
                                 push = (npix <= kMediumMaxPix) ? 1 : 2;
                                 entry = (uint32_t)(t + P.tri_base);
@@ -180,6 +196,48 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
             if (q == 1) qv[slot] = entry;
             else qv[P.Fq - 1 - slot] = entry;
         }
+    }
+}
+
+// All views of a vertex in one thread: the position is read once, B independent snap chains.
+__global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int B, int W, int H, SnapVert *sv)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= src.V) return;
+    const float *p = src.pos + 3 * (size_t)v;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    for (int b = 0; b < B; ++b) {
+        const float *m = src.mvp + 16 * b;
+        float4 c;
+        c.x = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
+        c.y = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
+        c.z = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
+        c.w = ((m[12] * x + m[13] * y) + m[14] * z) + m[15];
+        SnapVert s;
+        s.x = 0; s.y = 0; s.zw = 0.0f;
+        uint32_t flags = 0;
+        if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w)) flags |= WR_SV_FINITE;
+        uint32_t oc = 0;
+        oc |= (c.x < -c.w) ? 1u : 0u;
+        oc |= (c.x > c.w) ? 2u : 0u;
+        oc |= (c.y < -c.w) ? 4u : 0u;
+        oc |= (c.y > c.w) ? 8u : 0u;
+        oc |= (c.z < -c.w) ? 16u : 0u;
+        oc |= (c.z > c.w) ? 32u : 0u;
+        flags |= oc << WR_SV_OC_SHIFT;
+        if (c.w > 0.0f) {
+            const float rw = 1.0f / c.w;
+            const float fx = (c.x * (float)(8 * W)) * rw;
+            const float fy = (c.y * (float)(8 * H)) * rw;
+            if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
+                s.x = __float2int_rn(fx);
+                s.y = __float2int_rn(fy);
+                s.zw = c.z * rw;
+                flags |= WR_SV_OK;
+            }
+        }
+        s.flags = flags;
+        reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<int4 *>(&s);
     }
 }
 
@@ -305,10 +363,8 @@ struct WarpClipScratch {
 };
 
 template <bool LARGE>
-__global__ void __launch_bounds__(256) k_raster_queue(RasterParams P, VtxSrc src, int view0)
+__device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc &src, int b, WarpClipScratch *clip_smem)
 {
-    __shared__ WarpClipScratch clip_smem[LARGE ? 8 : 1];
-    const int b = blockIdx.y + view0;
     const unsigned lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long warps_total = (long long)gridDim.x * 8;
@@ -318,6 +374,7 @@ __global__ void __launch_bounds__(256) k_raster_queue(RasterParams P, VtxSrc src
     unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
     const long long items = LARGE ? (long long)count * kLargeStripes : (long long)count;
 
+#pragma unroll 1
     for (long long wi = gw; wi < items; wi += warps_total) {
         const int qi = LARGE ? (int)(wi / kLargeStripes) : (int)wi;
         const int stripe = LARGE ? (int)(wi % kLargeStripes) : 0;
@@ -365,9 +422,18 @@ __global__ void __launch_bounds__(256) k_raster_queue(RasterParams P, VtxSrc src
     }
 }
 
+// Medium queue (one warp per triangle) then large / clipped queue (32 warps per triangle) in one launch.
+__global__ void __launch_bounds__(256) k_raster_queues(RasterParams P, VtxSrc src, int view0)
+{
+    __shared__ WarpClipScratch clip_smem[8];
+    const int b = blockIdx.y + view0;
+    raster_queue<false>(P, src, b, clip_smem);
+    raster_queue<true>(P, src, b, clip_smem);
+}
+
 // (u, v, z/w) of the winning triangle at a pixel centre from the unsnapped clip-space vertices
 // (DESIGN.md 3.4).  Shared with the fused render kernel through common include below.
-__global__ void __launch_bounds__(256) k_resolve_rast(const unsigned long long *packed, VtxSrc src, const int32_t *tri,
+__global__ void __launch_bounds__(256) k_resolve_rast(unsigned long long *packed, VtxSrc src, const int32_t *tri,
                                                       int H, int W, float *rast, int32_t *tri_id)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,6 +445,7 @@ __global__ void __launch_bounds__(256) k_resolve_rast(const unsigned long long *
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     int id = -1;
     if (pk != WR_EMPTY_PIXEL) {
+        packed[o] = WR_EMPTY_PIXEL;  // self-cleaning: the next call skips the clear
         id = (int)(uint32_t)(pk & 0xFFFFFFFFull);
         const int i0 = __ldg(tri + 3 * (size_t)id), i1 = __ldg(tri + 3 * (size_t)id + 1), i2 = __ldg(tri + 3 * (size_t)id + 2);
         const float4 p0 = wr_load_clip(src, b, i0), p1 = wr_load_clip(src, b, i1), p2 = wr_load_clip(src, b, i2);
@@ -420,17 +487,25 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
     int rc = wr_scratch_reserve(ctx, total, stream);
     if (rc != WR_OK) return rc;
     char *base = static_cast<char *>(ctx->scratch);
-    SnapVert *sv = reinterpret_cast<SnapVert *>(base);
-    unsigned long long *depth = reinterpret_cast<unsigned long long *>(base + sv_bytes);
+    // the packed buffer sits at offset 0 so that its "known clean" prefix survives calls of any shape
+    unsigned long long *depth = reinterpret_cast<unsigned long long *>(base);
+    SnapVert *sv = reinterpret_cast<SnapVert *>(base + depth_bytes);
     uint32_t *queue = reinterpret_cast<uint32_t *>(base + sv_bytes + depth_bytes);
     int *stats = reinterpret_cast<int *>(base + sv_bytes + depth_bytes + queue_bytes);  // [B,4] counters + [B,4] user
     if (extra) *extra = base + sv_bytes + depth_bytes + queue_bytes + stats_bytes;
 
-    cudaError_t e = cudaMemsetAsync(depth, 0xFF, (size_t)B * H * W * sizeof(unsigned long long), stream);
-    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset depth");
+    wr_stage(ctx, stream, "clear");
+    const size_t packed_bytes = (size_t)B * H * W * sizeof(unsigned long long);
+    cudaError_t e;
+    if (ctx->clean_bytes < packed_bytes) {
+        e = cudaMemsetAsync(depth, 0xFF, packed_bytes, stream);
+        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset depth");
+    }
+    ctx->clean_bytes = 0;  // dirty until the consuming kernel has been launched
     e = cudaMemsetAsync(stats, 0, (size_t)B * 8 * sizeof(int), stream);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset counters");
     res->packed = depth;
+    res->packed_bytes = packed_bytes;
     res->view_stats = stats + 4 * B;
 
     if (F > 0 && V > 0 && B > 0) {
@@ -438,15 +513,19 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
         const int qgrid = ctx->sm_count * 2;
-        k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv);
+        wr_stage(ctx, stream, "k_snap_vertices");
+        if (src.mvp && !(ctx->tune & 2))
+            k_snap_vertices_allviews<<<wr_div_up(V, 256), 256, 0, stream>>>(src, B, W, H, sv);
+        else
+            k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv);
         WR_CHECK_LAUNCH(ctx, "k_snap_vertices");
         if (!tri_ranges) {
+            wr_stage(ctx, stream, "k_setup_triangles");
             k_setup_triangles<<<dim3(wr_div_up(F, 256), B), 256, 0, stream>>>(P, 0);
             WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
-            k_raster_queue<false><<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
-            WR_CHECK_LAUNCH(ctx, "k_raster_queue<medium>");
-            k_raster_queue<true><<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
-            WR_CHECK_LAUNCH(ctx, "k_raster_queue<large>");
+            wr_stage(ctx, stream, "k_raster_queues");
+            k_raster_queues<<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
+            WR_CHECK_LAUNCH(ctx, "k_raster_queues");
         } else {
             for (int b = 0; b < B; ++b) {
                 const int start = tri_ranges[2 * b], count = tri_ranges[2 * b + 1];
@@ -456,10 +535,8 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
                 Q.tri = tri + 3 * (size_t)start; Q.F = count; Q.tri_base = start;
                 k_setup_triangles<<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b);
                 WR_CHECK_LAUNCH(ctx, "k_setup_triangles(range)");
-                k_raster_queue<false><<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
-                WR_CHECK_LAUNCH(ctx, "k_raster_queue<medium>(range)");
-                k_raster_queue<true><<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
-                WR_CHECK_LAUNCH(ctx, "k_raster_queue<large>(range)");
+                k_raster_queues<<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
+                WR_CHECK_LAUNCH(ctx, "k_raster_queues(range)");
             }
         }
     }
@@ -479,11 +556,15 @@ extern "C" int wr_rasterize(wr_ctx *ctx, const float *pos, int B, int V, int pos
     VtxSrc src;
     src.pos = pos; src.mvp = nullptr; src.V = V; src.batched = pos_batched ? 1 : 0;
     RasterResult res;
+    wr_stage_begin(ctx);
     int rc = wr_run_raster(ctx, src, B, tri, F, tri_ranges, H, W, 0, &res, nullptr, stream);
     if (rc != WR_OK) return rc;
     if (rast || tri_id) {
+        wr_stage(ctx, stream, "k_resolve_rast");
         k_resolve_rast<<<dim3(wr_div_up(W, 256), H, B), 256, 0, stream>>>(res.packed, src, tri, H, W, rast, tri_id);
         WR_CHECK_LAUNCH(ctx, "k_resolve_rast");
+        wr_raster_consumed(ctx, &res);
     }
+    wr_stage(ctx, stream, "end");
     return WR_OK;
 }

@@ -290,7 +290,10 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         if tri_n.shape[0] != tri.shape[0]:
             raise ValueError("stitched_t_pos_idx must have one row per face of t_pos_idx")
         keep += [v_nrm, tri_n]
-        a.v_nrm, a.tri_nrm, a.Vn = _native.ptr(v_nrm), _native.ptr(tri_n), v_nrm.shape[0]
+        # a mesh that was not stitched shares one index tensor: the kernel then reuses the position indices
+        same_faces = mesh._stitched_t_pos_idx is None or mesh._stitched_t_pos_idx is mesh.t_pos_idx
+        a.v_nrm, a.Vn = _native.ptr(v_nrm), v_nrm.shape[0]
+        a.tri_nrm = None if same_faces else _native.ptr(tri_n)
         nbg = _background_triplet(normal_background, "normal_background")
         if nbg is None:
             nbg_tensor, nbg = normal_background, [0.0, 0.0, 0.0]
