@@ -159,3 +159,20 @@ def test_unsupported_options_raise(wr_ctx):
         proj(torch.from_numpy(images), mesh, cam, uv_size=64)  # defaults ask for Poisson blending + padding
     with pytest.raises(NotImplementedError):
         proj(torch.from_numpy(images), mesh, cam, uv_size=64, poisson_blending=False, uv_padding=True)
+
+
+def test_sharded_bake_single_process_equals_camera_projection(wr_ctx):
+    from worldrenderer_b200 import parallel
+    mesh, cam, images = _setup(wr_ctx.device)
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    want = proj(img, mesh, cam, uv_size=128, poisson_blending=False, uv_padding=False, iou_rejection_threshold=None,
+                return_dict=True)
+    atlas, any_ = parallel.sharded_bake(wr_ctx, mesh, cam, img, 128)
+    assert torch.equal(any_, want.uv_proj_mask)
+    torch.testing.assert_close(atlas, want.uv_proj, rtol=1e-5, atol=1e-6)
+    # a rank that owns no view contributes zeros
+    atlas0, any0 = parallel.sharded_bake(wr_ctx, mesh, cam[0:0], img[0:0], 128)
+    assert not bool(any0.any()) and torch.equal(atlas0, mesh.texture)
+    lo, outs = parallel.render_mesh_shard(wr_ctx, [mesh, mesh, mesh], cam, 64, 64, rank=1, world=2, render_attr=False)
+    assert lo == 2 and len(outs) == 1 and outs[0].mask.shape == (6, 64, 64)

@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference API (cameras, mesh loading, helpers) against outputs recorded from
+the unmodified reference (tests/golden, oracle/gen_golden.py), plus the C-ABI surface checks that need no
+GPU: libwr_b200.so loads and exports every function include/wr_b200.h declares."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import worldrenderer_b200 as wr
+from worldrenderer_b200 import _native, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def g(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def _cmp_cam(cam, gold, prefix):
+    for fld in ("c2w", "w2c", "proj_mtx", "mvp_mtx", "cam_pos"):
+        np.testing.assert_allclose(getattr(cam, fld).numpy(), gold[f"{prefix}_{fld}"], rtol=1e-6, atol=1e-6, err_msg=fld)
+
+
+def test_orthogonal_rig_matches_reference():
+    gold = g("cameras.npz")
+    cam = wr.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    _cmp_cam(cam, gold, "ortho")
+    assert len(cam) == 6 and cam.mvp_mtx.shape == (6, 4, 4)
+    assert cam.proj_mtx[0, 1, 1] < 0  # y is flipped in the projection (camera.py:104)
+
+
+def test_perspective_cameras_match_reference():
+    gold = g("cameras.npz")
+    cam = wr.get_camera(elevation_deg=[10.0, -20.0, 35.0, 60.0], distance=[1.8] * 4, fovy_deg=[40.0] * 4,
+                        azimuth_deg=[0.0, 75.0, 160.0, 250.0], aspect_wh=4 / 3, near=0.05, far=20.0)
+    _cmp_cam(cam, gold, "persp")
+    ring = wr.get_camera(elevation_deg=[0.0] * 3, distance=[2.0] * 3, fovy_deg=[50.0] * 3, azimuth_deg=None, num_views=3)
+    _cmp_cam(ring, gold, "ring")
+    # c2w given (Blender track of the reference's camera_path.json, rotation block scaled by 0.6)
+    cj = wr.get_camera(c2w=torch.from_numpy(gold["json_c2w"]), fovy_deg=torch.from_numpy(gold["json_fov"]), aspect_wh=720 / 480)
+    _cmp_cam(cj, gold, "json")
+    # w2c + projection given: no c2w, no camera position (camera.py:181-183)
+    ck = wr.get_camera(w2c=torch.linalg.inv(cam.c2w), proj_mtx=cam.proj_mtx)
+    assert ck.c2w is None and ck.cam_pos is None
+    np.testing.assert_allclose(ck.mvp_mtx.numpy(), gold["w2conly_mvp_mtx"], rtol=1e-6, atol=1e-6)
+
+
+def test_camera_indexing_semantics():
+    cam = wr.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    one = cam[2]
+    assert one.mvp_mtx.shape == (1, 4, 4) and torch.equal(one.mvp_mtx[0], cam.mvp_mtx[2])  # int keeps the batch dim
+    assert cam[1:3].w2c.shape == (2, 4, 4) and cam[[0, 5]].c2w.shape == (2, 4, 4)
+    with pytest.raises(NotImplementedError):
+        cam[(0, 1)]
+    torch.manual_seed(0)
+    a = torch.rand(1)
+    torch.manual_seed(0)
+    wr.get_camera(elevation_deg=[0.0], distance=[1.0], fovy_deg=[40.0], azimuth_deg=[0.0], perturb_camera_position=0.1)
+    b = torch.rand(1)
+    assert not torch.equal(a, b)  # the perturbation draws from the RNG like the reference (camera.py:170-178)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("default", {}),
+    ("rescale", dict(rescale=True)),
+    ("center_rescale", dict(rescale=True, move_to_center=True, scale=0.45)),
+    ("zup", dict(shape_init_mesh_up="+z", shape_init_mesh_front="-y", rescale=True)),
+    ("x2y", dict(front_x_to_y=True, rescale=True)),
+])
+def test_load_mesh_npz_matches_reference(tmp_path, name, kw):
+    gold = g("load_mesh.npz")
+    path = synth.save_npz(str(tmp_path / "m.npz"), gold["vertices"], gold["faces"])
+    mesh, off, sc = wr.load_mesh(path, return_transform=True, **kw)
+    np.testing.assert_allclose(mesh.v_pos.numpy(), gold[f"{name}_v_pos"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(mesh.t_pos_idx.numpy(), gold[f"{name}_t_pos_idx"])
+    assert mesh.t_pos_idx.dtype == torch.int64 and mesh.v_pos.dtype == torch.float32
+    assert (off is None) == (gold[f"{name}_offset"].size == 0)
+    if off is not None:
+        np.testing.assert_allclose(off, gold[f"{name}_offset"])
+    if sc is not None:
+        np.testing.assert_allclose(sc, gold[f"{name}_scale"])
+    assert mesh.v_tex is None and mesh.texture is None
+    assert mesh.stitched_t_pos_idx is mesh.t_pos_idx  # npz path: no vertex merging (mesh.py:222, 339-340)
+    with pytest.raises(RuntimeError):
+        mesh.v_nrm  # normals are a CUDA kernel; a CPU mesh must not silently take another path
+
+
+def test_load_mesh_argument_errors(tmp_path):
+    v, f = synth.icosphere(1)
+    path = synth.save_npz(str(tmp_path / "m.npz"), v, f)
+    with pytest.raises(ValueError):
+        wr.load_mesh(path, shape_init_mesh_up="+y", shape_init_mesh_front="-y")
+    with pytest.raises(ValueError):
+        wr.load_mesh(path, shape_init_mesh_up="up")
+
+
+def test_mesh_index_cache_invalidation():
+    v, f = synth.icosphere(1)
+    m = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f))
+    a = m.index_i32("t_pos_idx")
+    assert a.dtype == torch.int32 and m.index_i32("t_pos_idx") is a
+    m.t_pos_idx[0, 0] = 3  # in-place edit bumps the version counter
+    b = m.index_i32("t_pos_idx")
+    assert b is not a and int(b[0, 0]) == 3
+    m.t_pos_idx = m.t_pos_idx.clone()
+    assert m.index_i32("t_pos_idx") is not b
+
+
+def test_synthetic_configs_have_the_documented_sizes():
+    v, f = synth.icosphere(50)
+    assert f.shape == (50_000, 3) and v.shape == (25_002, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 0.5)
+    v, f = synth.terrain(100, 50)
+    assert f.shape == (10_000, 3) and v.shape == (101 * 51, 3)
+    vt, ft = synth.cell_atlas_uv(50_000)
+    assert vt.min() >= 0 and vt.max() <= 1 and ft.shape == (50_000, 3)
+
+
+def test_image_helpers():
+    im = Image.fromarray((np.arange(4 * 5 * 3).reshape(4, 5, 3) % 255).astype(np.uint8))
+    t = wr.image_to_tensor(im)
+    assert t.shape == (4, 5, 3) and t.dtype == torch.float32 and float(t.max()) <= 1.0
+    tb = wr.image_to_tensor([im, im])
+    assert tb.shape == (2, 4, 5, 3)
+    arr = np.full((2, 4, 5, 3), 7.0, np.float32)
+    assert float(wr.image_to_tensor(arr).max()) == 7.0  # arrays are not rescaled (utils.py:55-60)
+    back = wr.tensor_to_image(t)
+    assert back.size == (5, 4)
+    grid = wr.make_image_grid([back] * 6)
+    assert grid.size == (15, 8)
+    pts = torch.randn(2, 3, 4, 3)
+    mtx = torch.randn(2, 4, 4)
+    homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1)
+    want = torch.einsum("bij,bhwj->bhwi", mtx, homo)[..., :3]
+    torch.testing.assert_close(wr.transform_points_homo(pts, mtx), want, rtol=1e-5, atol=1e-5)
+    clip = wr.get_clip_space_position(pts[0].reshape(-1, 3), mtx)
+    assert clip.shape == (2, 12, 4)
+
+
+def test_normalisers_on_tensors_match_reference_formulas():
+    d = torch.tensor([[[1.0, 2.0], [3.0, 5.0]]])
+    m = torch.tensor([[[True, True], [True, False]]])
+    out = wr.DepthControlNetNormalization()(d.clone(), m)
+    want = (1 - (d - 1) / (4 + 1e-5)) * 0.75 + 0.25
+    assert torch.allclose(out[m], want[m]) and float(out[0, 1, 1]) == 0.0
+    out = wr.SimpleNormalization(scale=0.5, offset=-0.25)(d.clone(), m)
+    assert torch.allclose(out[m], (d * 0.5 - 0.25).clamp(0, 1)[m]) and float(out[0, 1, 1]) == 1.0
+    out = wr.Zero123PlusPlusNormalization()(d.clone(), m)
+    assert abs(float(out[0, 1, 1]) - 0.8) < 1e-7
+
+
+def test_no_cpu_path():
+    with pytest.raises(RuntimeError):
+        wr.NVDiffRastContextWrapper("cpu", "cuda")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            wr.NVDiffRastContextWrapper("cuda:0", "cuda")
+    with pytest.raises(NotImplementedError):
+        wr.SmartPainter()
+    with pytest.raises(NotImplementedError):
+        wr.replace_mesh_texture_and_save()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "wr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from worldrenderer_b200 import build_native
+    lib = build_native.build()
+    declared = _declared_functions()
+    assert len(declared) >= 15
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (wr_[a-z0-9_]+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert sorted(_native.SYMBOLS) == declared  # the Python binding covers the whole header
+    L = _native.lib()  # dlopen works without a GPU (no compute call is made)
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.wr_version() >= 100
+    assert L.wr_status_string(-5).decode() == "unsupported configuration"
+
+
+def test_library_is_sm100a_only_and_fmad_free_on_the_contract_path():
+    from worldrenderer_b200 import build_native
+    assert "-fmad=false" in build_native.NVCC_FLAGS
+    assert any("compute_100a" in f for f in build_native.NVCC_FLAGS)
+    lib = build_native.build()
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
