@@ -141,15 +141,19 @@ def cpu_render_setup(seed: int = 0):
     return v, f32, v_nrm, cam.mvp_mtx.numpy(), cam.w2c.numpy()
 
 
+def cpu_threads() -> int:
+    """Host threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    so the count is passed to the oracle explicitly instead of being left to the OpenMP default)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_render_step(state, views: int = N_VIEWS):
     from oracle import render_oracle
     v, f32, v_nrm, mvp, w2c = state
-    return render_oracle.render(v, f32, mvp[:views], w2c[:views], H, W, v_nrm=v_nrm)
-
-
-def cpu_threads() -> int:
-    from oracle import shim
-    return shim.num_threads()
+    return render_oracle.render(v, f32, mvp[:views], w2c[:views], H, W, v_nrm=v_nrm, nthreads=cpu_threads())
 
 
 def run_reference(args):

@@ -65,3 +65,24 @@ if args.bake:
     with torch.no_grad():
         b = bench.bench_bake(ctx, dev, flush)
     print(b)
+    from worldrenderer_b200.uv import fused_view_maps, fused_unproject
+    import contextlib, io
+    v, f = synth.icosphere(50, 0.5)
+    vt, ft = synth.cell_atlas_uv(f.shape[0])
+    m = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f), v_tex=torch.tensor(vt, dtype=torch.float32),
+                        t_tex_idx=torch.tensor(ft), texture=torch.zeros((1024, 1024, 3)))
+    m.set_stitched_mesh(m.v_pos, m.t_pos_idx); m.to(dev); m.v_nrm
+    images = torch.from_numpy(synth.view_images(6, 768, 768, seed=1)).to(dev)
+    pre = wr.uv_precompute(ctx, m, 1024, 1024)
+    ctx.ctx.profile(True)
+    acc = {}
+    for k in range(8):
+        flush.fill_(k)
+        wr.uv_precompute(ctx, m, 1024, 1024)
+        for n, ms in ctx.ctx.profile_read(): acc.setdefault("pre:" + n, []).append(ms * 1e3)
+        _, geo, att = fused_view_maps(ctx, m, cam, images, 768, 768, 5)
+        for n, ms in ctx.ctx.profile_read(): acc.setdefault("prep:" + n, []).append(ms * 1e3)
+        fused_unproject(ctx, pre, cam, 768, 768, geo, att, aoi_cos_thresh=0.2, depth_grad_thresh=0.1, alpha=3.0)
+        for n, ms in ctx.ctx.profile_read(): acc.setdefault("unproj:" + n, []).append(ms * 1e3)
+    ctx.ctx.profile(False)
+    print("bake stages (us):", {n: round(float(np.mean(x[2:])), 1) for n, x in acc.items()})

@@ -3,8 +3,8 @@
 // branch), driven by projection.py:54-204.  The reference materialises ~10 [Nv,Huv,Wuv,*] tensors; here
 // one kernel walks the views per texel and keeps everything in registers.
 //
-//   k_view_aoi_sobel   per view pixel: camera-space normal -> aoi_cos, zero-padded Sobel magnitude
-//   k_dilate_pack      per view pixel: d x d max-pool of the gradient; packs two float4 maps
+//   k_view_prep        per view pixel (32x8 tiles, shared memory): camera-space normal -> aoi_cos, zero-padded
+//                      Sobel magnitude, separable d x d max-pool; packs two float4 maps
 //                      geo = (pos.xyz, aoi_cos), attr = (rgb, depth_grad) so that a bilinear sample is
 //                      4 taps x 2 x 16-byte loads instead of 4 taps x (12 + 4 + 4 + 12) bytes
 //   k_uv_unproject     per texel: project into every view, gather, validity, weight, accumulate
@@ -13,71 +13,88 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) k_view_aoi_sobel(const float *normal, const uint8_t *mask, const float *depth,
-                                                        const float *w2c, int H, int W, int want_grad, float *aoi_out,
-                                                        float *g_out)
+// View side of the bake in one pass.  A 32x8 output tile per block; the depth tile (halo pad+1, zeros
+// outside the image = conv2d zero padding), the Sobel magnitude (halo pad, -inf outside the image =
+// max_pool2d padding) and the row maxima live in shared memory, so a pixel costs ~3 global loads instead
+// of the 9 + d*d of the two-kernel form (measured 102 us -> see profiles/README.md on config C).
+constexpr int kPrepTW = 32, kPrepTH = 8;
+
+__global__ void __launch_bounds__(kPrepTW * kPrepTH) k_view_prep(const float *normal, const uint8_t *mask,
+                                                                const float *depth, const float *position,
+                                                                const float *w2c, const float *images, int H, int W,
+                                                                int dilation, float *aoi_out, float *depth_grad,
+                                                                float *geo_map, float *attr_map)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y, b = blockIdx.z;
-    if (c >= W) return;
+    extern __shared__ float smem[];
+    const int pad = dilation / 2;              // max-pool halo
+    const int hd = pad + 1;                    // depth halo (Sobel needs one more ring)
+    const int dw = kPrepTW + 2 * hd, dh = kPrepTH + 2 * hd;
+    const int gw = kPrepTW + 2 * pad, gh = kPrepTH + 2 * pad;
+    float *s_d = smem;                         // [dh][dw]
+    float *s_g = s_d + dh * dw;                // [gh][gw]
+    float *s_r = s_g + gh * gw;                // [gh][kPrepTW] row maxima
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * kPrepTW, y0 = blockIdx.y * kPrepTH;
+    const int tid = threadIdx.y * kPrepTW + threadIdx.x;
+    const int nthreads = kPrepTW * kPrepTH;
+    float dg = 0.0f;
+    if (dilation > 0) {
+        const float *dv = depth + (size_t)b * H * W;
+        for (int i = tid; i < dh * dw; i += nthreads) {
+            const int yy = y0 - hd + i / dw, xx = x0 - hd + i % dw;
+            s_d[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
+        }
+        __syncthreads();
+        for (int i = tid; i < gh * gw; i += nthreads) {
+            const int gy_ = i / gw, gx_ = i % gw;
+            const int yy = y0 - pad + gy_, xx = x0 - pad + gx_;
+            float g = -INFINITY;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const float *c = s_d + (gy_ + 1) * dw + (gx_ + 1);  // centre of the 3x3 window in the depth tile
+                const float s00 = c[-dw - 1], s01 = c[-dw], s02 = c[-dw + 1];
+                const float s10 = c[-1], s12 = c[1];
+                const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
+                const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
+                const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
+                g = sqrtf(gx * gx + gy * gy);
+            }
+            s_g[i] = g;
+        }
+        __syncthreads();
+        for (int i = tid; i < gh * kPrepTW; i += nthreads) {
+            const int ry = i / kPrepTW, rx = i % kPrepTW;
+            const float *row = s_g + ry * gw + rx;
+            float m = row[0];
+            for (int k = 1; k < dilation; ++k) m = fmaxf(m, row[k]);
+            s_r[i] = m;
+        }
+        __syncthreads();
+        const float *col = s_r + threadIdx.y * kPrepTW + threadIdx.x;
+        dg = col[0];
+        for (int k = 1; k < dilation; ++k) dg = fmaxf(dg, col[k * kPrepTW]);
+    }
+    const int c = x0 + threadIdx.x, r = y0 + threadIdx.y;
+    if (c >= W || r >= H) return;
     const size_t o = ((size_t)b * H + r) * W + c;
     const float *n = normal + 3 * o;
     const float nx = n[0], ny = n[1], nz = n[2];
     float aoi;
     if (mask[o]) {
         const float *R = w2c + 16 * b;
-        float x = (R[0] * nx + R[1] * ny) + R[2] * nz;
-        float y = (R[4] * nx + R[5] * ny) + R[6] * nz;
-        float z = (R[8] * nx + R[9] * ny) + R[10] * nz;
+        const float x = (R[0] * nx + R[1] * ny) + R[2] * nz;
+        const float y = (R[4] * nx + R[5] * ny) + R[6] * nz;
+        const float z = (R[8] * nx + R[9] * ny) + R[10] * nz;
         const float ln = sqrtf((x * x + y * y) + z * z);
-        z = z / fmaxf(ln, 1e-12f);
-        aoi = z;
+        aoi = z / fmaxf(ln, 1e-12f);
     } else {
         aoi = nz;  // uv.py:112: background keeps the render's normal (normal_background)
     }
     aoi = fminf(fmaxf(aoi, 0.0f), 1.0f);
-    aoi_out[o] = aoi;
-    if (want_grad) {
-        const float *d = depth + (size_t)b * H * W;
-        auto at = [&](int rr, int cc) -> float {
-            return (rr >= 0 && rr < H && cc >= 0 && cc < W) ? __ldg(d + (size_t)rr * W + cc) : 0.0f;
-        };
-        const float s00 = at(r - 1, c - 1), s01 = at(r - 1, c), s02 = at(r - 1, c + 1);
-        const float s10 = at(r, c - 1), s12 = at(r, c + 1);
-        const float s20 = at(r + 1, c - 1), s21 = at(r + 1, c), s22 = at(r + 1, c + 1);
-        const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
-        const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
-        g_out[o] = sqrtf(gx * gx + gy * gy);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_dilate_pack(const float *aoi, const float *g, const float *position,
-                                                     const float *images, int H, int W, int dilation, float *depth_grad,
-                                                     float *geo_map, float *attr_map)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y, b = blockIdx.z;
-    if (c >= W) return;
-    const size_t o = ((size_t)b * H + r) * W + c;
-    float dg = 0.0f;
-    if (dilation > 0) {
-        const int pad = dilation / 2;
-        const float *gv = g + (size_t)b * H * W;
-        dg = -INFINITY;
-        for (int dy = -pad; dy <= pad; ++dy) {
-            const int rr = r + dy;
-            if (rr < 0 || rr >= H) continue;
-            for (int dx = -pad; dx <= pad; ++dx) {
-                const int cc = c + dx;
-                if (cc < 0 || cc >= W) continue;
-                dg = fmaxf(dg, __ldg(gv + (size_t)rr * W + cc));
-            }
-        }
-        if (depth_grad) depth_grad[o] = dg;
-    }
+    if (aoi_out) aoi_out[o] = aoi;
+    if (dilation > 0 && depth_grad) depth_grad[o] = dg;
     if (geo_map) {
         const float *p = position + 3 * o;
-        reinterpret_cast<float4 *>(geo_map)[o] = make_float4(p[0], p[1], p[2], aoi[o]);
+        reinterpret_cast<float4 *>(geo_map)[o] = make_float4(p[0], p[1], p[2], aoi);
     }
     if (attr_map) {
         float rr = 0.f, gg = 0.f, bb = 0.f;
@@ -172,15 +189,16 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A, int m
             const float gx = cx / cw, gy = cy / cw;  // uv.py:90, no w > 0 guard
             const Bilinear t = make_bilinear(gx, gy, A.W, A.H);
             const float4 geo = sample4(reinterpret_cast<const float4 *>(A.geo_map) + v * npix, t, A.W, A.H);
-            float4 att = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (A.attr_map) att = sample4(reinterpret_cast<const float4 *>(A.attr_map) + v * npix, t, A.W, A.H);
             const float dx = geo.x - ux, dy = geo.y - uy, dz = geo.z - uz;
             const float err = sqrtf((dx * dx + dy * dy) + dz * dz);
-            bool valid = (err < A.pos_error_eps) && (geo.w > A.aoi_cos_thresh);
+            bool valid = (err < A.pos_error_eps) && (geo.w > A.aoi_cos_thresh) && inside;
+            // the colour / depth-gradient taps only matter for a texel that passed the geometry test
+            float4 att = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (A.attr_map && (valid || materialise))
+                att = sample4(reinterpret_cast<const float4 *>(A.attr_map) + v * npix, t, A.W, A.H);
             if (A.use_depth_grad) valid = valid && (att.w < A.depth_grad_thresh);
-            valid = valid && inside;
             float mp = 0.f;
-            if (A.view_masks) {
+            if (A.view_masks && (valid || materialise)) {
                 mp = sample1(A.view_masks + v * npix, t, A.W, A.H);
                 valid = valid && (mp > A.mask_thresh);
             }
@@ -189,7 +207,8 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A, int m
                 else valid = valid && !valid0;
             }
             float wgt = geo.w * (valid ? 1.0f : 0.0f);
-            wgt = powf(wgt, s_expo[v]);
+            // pow(0, e) is 0 for e > 0 (the common case of an invalid view): skip the call
+            wgt = (wgt == 0.0f && s_expo[v] > 0.0f) ? 0.0f : powf(wgt, s_expo[v]);
             sw = sw + wgt;
             sr = sr + att.x * wgt; sg = sg + att.y * wgt; sb = sb + att.z * wgt;
             nvalid += valid ? 1 : 0;
@@ -309,31 +328,17 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
-    const size_t n = (size_t)B * H * W;
-    float *aoi_buf = aoi_cos, *g_buf = nullptr;
-    size_t need = 0;
-    if (!aoi_buf) need += wr_align256(n * sizeof(float));
-    if (dilation > 0) need += wr_align256(n * sizeof(float));
-    if (need) {
-        int rc = wr_scratch_reserve(ctx, need, stream);
-        if (rc != WR_OK) return rc;
-        ctx->clean_bytes = 0;  // the temporaries overwrite the raster's packed buffer
-        char *p = static_cast<char *>(ctx->scratch);
-        if (!aoi_buf) { aoi_buf = reinterpret_cast<float *>(p); p += wr_align256(n * sizeof(float)); }
-        if (dilation > 0) g_buf = reinterpret_cast<float *>(p);
-    }
-    const dim3 grid(wr_div_up(W, 256), H, B);
-    // dilation 1 is the identity max-pool: write the gradient straight through the second kernel as well
+    const int pad = dilation / 2, hd = pad + 1;
+    const size_t smem = sizeof(float) * ((size_t)(kPrepTH + 2 * hd) * (kPrepTW + 2 * hd) +
+                                         (size_t)(kPrepTH + 2 * pad) * (kPrepTW + 2 * pad) +
+                                         (size_t)(kPrepTH + 2 * pad) * kPrepTW);
+    if (smem > 48 * 1024) return WR_ERR_UNSUPPORTED;  // dilation > ~60
+    const dim3 grid(wr_div_up(W, kPrepTW), wr_div_up(H, kPrepTH), B);
     wr_stage_begin(ctx);
-    wr_stage(ctx, stream, "k_view_aoi_sobel");
-    k_view_aoi_sobel<<<grid, 256, 0, stream>>>(normal, mask, depth, w2c, H, W, dilation > 0, aoi_buf, g_buf);
-    WR_CHECK_LAUNCH(ctx, "k_view_aoi_sobel");
-    if (depth_grad || geo_map || attr_map) {
-        wr_stage(ctx, stream, "k_dilate_pack");
-        k_dilate_pack<<<grid, 256, 0, stream>>>(aoi_buf, g_buf, position, images, H, W, dilation, depth_grad, geo_map,
-                                               attr_map);
-        WR_CHECK_LAUNCH(ctx, "k_dilate_pack");
-    }
+    wr_stage(ctx, stream, "k_view_prep");
+    k_view_prep<<<grid, dim3(kPrepTW, kPrepTH), dilation > 0 ? smem : 0, stream>>>(
+        normal, mask, depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map);
+    WR_CHECK_LAUNCH(ctx, "k_view_prep");
     wr_stage(ctx, stream, "end");
     return WR_OK;
 }

@@ -23,7 +23,7 @@ from .camera import Camera, get_camera
 from .mesh import TexturedMesh
 from .render import NVDiffRastContextWrapper
 from .utils import IMAGE_TYPE, LIST_TYPE, image_to_tensor
-from .uv import fused_unproject, fused_view_maps, uv_precompute
+from .uv import UVPrecomputeOutput, fused_unproject, fused_view_maps, uv_precompute
 
 
 @dataclass
@@ -44,6 +44,21 @@ class CameraProjection:
         self.ctx = NVDiffRastContextWrapper(device, context_type)
         self.bg_remover = bg_remover
         self.device = device
+        self._pre_cache = None  # (key, tensors kept alive, uv_mask, uv_pos)
+
+    def _uv_precompute(self, mesh: TexturedMesh, uv_size: int) -> UVPrecomputeOutput:
+        """uv_precompute (uv.py:24-53) depends on the mesh and the atlas size only; the reference recomputes it on
+        every call, here the last result is reused while the mesh tensors are unchanged (same storage, same
+        version counter).  The texture is always taken fresh from the mesh."""
+        srcs = (mesh.v_pos, mesh.t_pos_idx, mesh.v_tex, mesh.t_tex_idx)
+        key = (int(uv_size),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+        if self._pre_cache is not None and self._pre_cache[0] == key:
+            _, _, uv_mask, uv_pos = self._pre_cache
+        else:
+            pre = uv_precompute(self.ctx, mesh, height=uv_size, width=uv_size)
+            uv_mask, uv_pos = pre.uv_mask, pre.uv_pos
+            self._pre_cache = (key, srcs, uv_mask, uv_pos)  # srcs kept alive so a pointer cannot be recycled
+        return UVPrecomputeOutput(height=uv_size, width=uv_size, uv_attr=mesh.texture, uv_mask=uv_mask, uv_pos=uv_pos)
 
     def __call__(
         self,
@@ -105,7 +120,7 @@ class CameraProjection:
             cam = get_camera(elevation_deg, distance, fovy_deg, azimuth_deg, num_views, c2w, aspect_wh=W / H,
                              device=self.device)
 
-        pre = uv_precompute(self.ctx, mesh, height=uv_size, width=uv_size)
+        pre = self._uv_precompute(mesh, uv_size)
         view_mask, geo_map, attr_map = fused_view_maps(self.ctx, mesh, cam, images_pt, H, W,
                                                        int(depth_grad_dilation))
 
