@@ -44,8 +44,6 @@ extern "C" int wr_ctx_create(int device, wr_ctx **out)
     if (!ctx) return WR_ERR_OUT_OF_MEMORY;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    const char *tune = getenv("WR_TUNE");
-    ctx->tune = tune ? atoi(tune) : 0;
     *out = ctx;
     return WR_OK;
 }

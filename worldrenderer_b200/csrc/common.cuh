@@ -75,7 +75,6 @@ struct wr_ctx {
     size_t scratch_bytes;
     char last_error[256];
     size_t clean_bytes;  // leading bytes of scratch (the packed depth/id buffer) known to be all 0xFF
-    int tune;  // experiment switches (env WR_TUNE), see csrc/raster.cu
     // optional per-stage timing (bench.py): events recorded on the launch stream between kernels
     int profiling;
     int n_marks;

@@ -514,7 +514,7 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
         const int qgrid = ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
-        if (src.mvp && !(ctx->tune & 2))
+        if (src.mvp)
             k_snap_vertices_allviews<<<wr_div_up(V, 256), 256, 0, stream>>>(src, B, W, H, sv);
         else
             k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv);
