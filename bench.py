@@ -366,8 +366,13 @@ def run_ours(args):
         roofline = None
         if dom is not None:
             achieved = ab[dom] * N_VIEWS / (kernel_stages[dom] * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    traffic = json.load(fh).get(dom)  # DRAM bytes per launch of this kernel from the committed ncu capture
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": ab[dom] * N_VIEWS, "kernel_ms": kernel_stages[dom],
                         "share_of_step": kernel_stages[dom] / max(sum(stages.values()), 1e-9)}
         ms_per_step = total_ms_max / K

@@ -176,3 +176,21 @@ def test_sharded_bake_single_process_equals_camera_projection(wr_ctx):
     assert not bool(any0.any()) and torch.equal(atlas0, mesh.texture)
     lo, outs = parallel.render_mesh_shard(wr_ctx, [mesh, mesh, mesh], cam, 64, 64, rank=1, world=2, render_attr=False)
     assert lo == 2 and len(outs) == 1 and outs[0].mask.shape == (6, 64, 64)
+
+
+def test_config_c_full_size_against_oracle(wr_ctx):
+    """BASELINE config C at full size: 50k-face icosphere, 6 x 768^2 images -> 1024^2 atlas."""
+    mesh, cam, images = _setup(wr_ctx.device, freq=50, views=(768, 768), uv_size=1024)
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    vw = torch.ones(6)
+    out = proj(torch.from_numpy(images), mesh, cam, uv_size=1024, poisson_blending=False, uv_padding=False,
+               depth_grad_dilation=5, uv_exp_blend_alpha=3, uv_exp_blend_view_weight=vw, aoi_cos_valid_threshold=0.2,
+               depth_grad_threshold=0.1, iou_rejection_threshold=None, return_dict=True)
+    ref = _oracle_bake(mesh, cam, images, 1024, aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
+                       uv_exp_blend_alpha=3.0, uv_exp_blend_view_weight=vw.numpy(), depth_grad_dilation=5)
+    stable = ~_near_threshold(ref, 0.2, 0.1)
+    assert stable.mean() > 0.995
+    np.testing.assert_array_equal(out.uv_proj_mask.cpu().numpy()[stable], ref["uv_proj_mask"][stable])
+    np.testing.assert_allclose(out.uv_proj.cpu().numpy()[stable], ref["uv_proj"][stable], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(out.uv_aoi_cos.cpu().numpy(), ref["uv_aoi_cos"], rtol=RTOL, atol=ATOL)
+    assert ref["uv_proj_mask"].sum() > 200_000

@@ -205,3 +205,23 @@ def test_config_e_scale_runs_and_is_consistent(wr_ctx):
     diff = (hi_pos[both] - lo["pos"][both]).abs().max(dim=-1).values
     assert float((diff < 5e-3).float().mean()) > 0.97  # the rest sit on occlusion edges of the relief
     assert wr_ctx.ctx.scratch_bytes() < 2 << 30
+
+
+def test_config_b_full_size_bit_exact_ids_against_oracle(wr_ctx):
+    """BASELINE config B at full size: 1M-face terrain, canonical 6-view rig, 768^2 -- triangle ids and masks
+    bit-exact, position / normal / depth within 1e-5 against the CPU oracle (about 2 s of host time)."""
+    from worldrenderer_b200 import synth
+    v, f = synth.terrain(1000, 500, 0)
+    v = v / np.abs(v).max() * 0.5
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1).astype(np.float32)
+    mesh = make_mesh(v, f.astype(np.int32), wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    raw = render_geometry_raw(wr_ctx, mesh, cam, 768, 768, want_tri_id=True,
+                              depth_normalization_strategy=wr.DepthControlNetNormalization())
+    ref = _oracle(mesh, cam, 768, 768, DepthSpec("controlnet"))
+    np.testing.assert_array_equal(raw["tri_id"].cpu().numpy(), ref["tri_id"])
+    np.testing.assert_array_equal(raw["mask"].cpu().numpy(), ref["mask"])
+    np.testing.assert_allclose(raw["pos"].cpu().numpy(), ref["pos"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(raw["normal"].cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(raw["depth"].cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
+    assert ref["mask"].sum() > 700_000
