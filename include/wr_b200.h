@@ -25,6 +25,7 @@
  *                                    uv_render_attr uv.py:193-222, SimpleUVValidityStrategy
  *                                    uv.py:248-298, ExponentialBlend uv.py:317-348, the view sum of
  *                                    uv_blend uv.py:411,421-423
+ *   wr_uv_reduce_finalize_p2p        (new) the bake's exchange step fused with finalisation over NVLink peer memory
  *   wr_grid_sample                   F.grid_sample as used by uv_render_attr uv.py:200-218 (operator form)
  *   wr_uv_finalize                   hard stitch with the existing texture uv.py:452-455 (after the
  *                                    optional multi-GPU all-reduce of the accumulators)
@@ -185,6 +186,24 @@ int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void *stream);
 /* out = valid_any ? accum.rgb / max(accum.w, 1e-5) : old ; valid_any = accum.valid > 0 */
 int wr_uv_finalize(wr_ctx *ctx, const float *accum, const float *old_attr, int Hu, int Wu, float *out_attr,
                    uint8_t *out_valid_any, void *stream);
+
+/*
+ * Multi-GPU bake (no reference counterpart; the reference is single-GPU): fused reduce-scatter + finalise +
+ * all-gather of the accumulators through peer-mapped device memory (NVLink / NVSwitch).  accum[r],
+ * out_attr[r], out_valid[r] are THIS process's mappings of rank r's buffers ([Hu,Wu,5] f32, [Hu,Wu,3] f32,
+ * [Hu,Wu] u8; 16-byte aligned).  The caller must make sure every rank has finished writing its accumulators
+ * before the call (device-side barrier) and must not read its atlas before a second barrier after it.
+ * Result: identical on every rank; equals wr_uv_finalize of the rank-ordered sum.  Hu*Wu must be a multiple of 4.
+ */
+#define WR_MAX_P2P_RANKS 16
+typedef struct wr_p2p_reduce_args {
+    const float *accum[WR_MAX_P2P_RANKS];
+    float *out_attr[WR_MAX_P2P_RANKS];
+    uint8_t *out_valid[WR_MAX_P2P_RANKS];
+    const float *old_attr;    /* local [Hu,Wu,3] or NULL (same texture on every rank) */
+    int world, rank, Hu, Wu;
+} wr_p2p_reduce_args;
+int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *args, void *stream);
 
 /*
  * F.grid_sample(mode="bilinear", padding_mode="zeros", align_corners=False) on channels-last maps

@@ -36,15 +36,50 @@ ctx = wr.NVDiffRastContextWrapper(str(dev), "cuda")
 
 lo, hi = parallel.my_shard(nv)
 kw = dict(aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1, uv_exp_blend_alpha=3.0)
-atlas, any_ = parallel.sharded_bake(ctx, mesh, cam[lo:hi], images[lo:hi], uv, **kw)
-torch.cuda.synchronize()
-dist.barrier()
-t0 = time.perf_counter()
-for _ in range(5):
-    atlas, any_ = parallel.sharded_bake(ctx, mesh, cam[lo:hi], images[lo:hi], uv, **kw)
-torch.cuda.synchronize()
-dist.barrier()
-ms = (time.perf_counter() - t0) / 5 * 1e3
+timing = {}
+results = {}
+for mode in ("nccl", "p2p"):
+    a_, m_ = parallel.sharded_bake(ctx, mesh, cam[lo:hi], images[lo:hi], uv, exchange=mode, **kw)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        a_, m_ = parallel.sharded_bake(ctx, mesh, cam[lo:hi], images[lo:hi], uv, exchange=mode, **kw)
+    torch.cuda.synchronize()
+    dist.barrier()
+    timing[mode] = (time.perf_counter() - t0) / 10 * 1e3
+    results[mode] = (a_.clone(), m_.clone())
+p2p_vs_nccl = float((results["p2p"][0] - results["nccl"][0]).abs().max())
+p2p_mask_same = torch.equal(results["p2p"][1], results["nccl"][1])
+atlas, any_ = results["p2p"]
+ms = timing["p2p"]
+
+# exchange step alone at the atlas sizes of configs C / E: NCCL all_reduce + finalize vs the fused peer-memory kernel
+from worldrenderer_b200.uv import uv_finalize
+exch = {}
+for size in (1024, 2048, 4096):
+    ws = parallel._p2p_workspace(size, size, dev, None)
+    acc = torch.rand((size, size, 5), device=dev)
+    old = torch.zeros((size, size, 3), device=dev)
+    ws.accum.copy_(acc)
+    def run_nccl():
+        t = acc.clone()
+        parallel.all_reduce_accumulators(t)
+        return uv_finalize(ctx, t, old)
+    def run_p2p():
+        return ws.reduce_finalize(ctx, old)
+    for name, fn in (("nccl", run_nccl), ("p2p", run_p2p)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exch[(size, name)] = float(t)
 
 # every rank also computes the full single-GPU bake and compares
 proj = wr.CameraProjection(None, None, str(dev), "cuda")
@@ -54,7 +89,7 @@ with contextlib.redirect_stdout(io.StringIO()):
                 depth_grad_dilation=5, return_dict=True, **kw)
 ok_mask = torch.equal(any_, full.uv_proj_mask)
 err = float((atlas - full.uv_proj).abs().max())
-ok = ok_mask and err < 1e-5
+ok = ok_mask and err < 1e-5 and p2p_mask_same and p2p_vs_nccl < 1e-5
 # all ranks must hold the same atlas bit for bit
 gathered = [torch.empty_like(atlas) for _ in range(world)]
 dist.all_gather(gathered, atlas)
@@ -67,7 +102,11 @@ first, outs = parallel.render_mesh_shard(ctx, [mesh] * 4, cam, 256, 256, render_
 n_local = torch.tensor([len(outs)], device=dev)
 dist.all_reduce(n_local)
 if rank == 0:
-    print(f"world={world} views={nv} sharded_bake_ms={ms:.3f} mask_equal={ok_mask} max_abs_err={err:.2e} "
+    print(f"world={world} views={nv} sharded_bake_ms p2p={timing['p2p']:.3f} nccl={timing['nccl']:.3f} mask_equal={ok_mask} "
+          f"max_abs_err={err:.2e} p2p_vs_nccl_max_abs={p2p_vs_nccl:.2e} p2p_mask_same={p2p_mask_same} "
           f"ranks_identical={same} meshes_rendered={int(n_local)} covered_texels={int(any_.sum())}")
+    for size in (1024, 2048, 4096):
+        print(f"exchange step atlas {size}^2: nccl all_reduce+finalize {exch[(size, 'nccl')]:.3f} ms, "
+              f"fused p2p kernel {exch[(size, 'p2p')]:.3f} ms")
     print("PASS" if int(flag) == 1 and int(n_local) == 4 else "FAIL")
 dist.destroy_process_group()

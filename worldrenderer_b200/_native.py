@@ -22,7 +22,7 @@ _LIB: Optional[ctypes.CDLL] = None
 SYMBOLS = [
     "wr_status_string", "wr_ctx_last_error", "wr_version", "wr_ctx_create", "wr_ctx_destroy",
     "wr_ctx_scratch_bytes", "wr_ctx_profile", "wr_ctx_profile_read", "wr_ctx_profile_stage_name", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
-    "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample",
+    "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample", "wr_uv_reduce_finalize_p2p",
 ]
 
 DEPTH_NONE, DEPTH_CONTROLNET, DEPTH_ZERO123PP, DEPTH_SIMPLE = 0, 1, 2, 3
@@ -60,6 +60,17 @@ class UnprojectArgs(ctypes.Structure):
         ("uv_aoi_cos", ctypes.c_void_p), ("uv_depth_grad", ctypes.c_void_p), ("uv_attr_proj", ctypes.c_void_p),
         ("uv_mask_proj", ctypes.c_void_p), ("uv_valid", ctypes.c_void_p), ("uv_weight", ctypes.c_void_p),
         ("old_attr", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_valid_any", ctypes.c_void_p),
+    ]
+
+
+MAX_P2P_RANKS = 16
+
+
+class P2PReduceArgs(ctypes.Structure):
+    _fields_ = [
+        ("accum", ctypes.c_void_p * MAX_P2P_RANKS), ("out_attr", ctypes.c_void_p * MAX_P2P_RANKS),
+        ("out_valid", ctypes.c_void_p * MAX_P2P_RANKS), ("old_attr", ctypes.c_void_p),
+        ("world", ctypes.c_int), ("rank", ctypes.c_int), ("Hu", ctypes.c_int), ("Wu", ctypes.c_int),
     ]
 
 
@@ -107,6 +118,8 @@ def lib() -> ctypes.CDLL:
     L.wr_uv_unproject.argtypes = [vp, ctypes.POINTER(UnprojectArgs), vp]
     L.wr_uv_finalize.restype = ci
     L.wr_uv_finalize.argtypes = [vp, vp, vp, ci, ci, vp, vp, vp]
+    L.wr_uv_reduce_finalize_p2p.restype = ci
+    L.wr_uv_reduce_finalize_p2p.argtypes = [vp, ctypes.POINTER(P2PReduceArgs), vp]
     L.wr_grid_sample.restype = ci
     L.wr_grid_sample.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp, vp]
     _LIB = L

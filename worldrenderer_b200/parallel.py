@@ -16,11 +16,14 @@ BASELINE.json asks for:
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+import ctypes
+import warnings
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
+from . import _native
 from .camera import Camera
 
 
@@ -78,23 +81,108 @@ def render_mesh_shard(ctx, meshes: Sequence, cam: Camera, height: int, width: in
     return lo, [render(ctx, meshes[i], cam, height, width, **render_kwargs) for i in range(lo, hi)]
 
 
+class P2PBakeWorkspace:
+    """Peer-mapped (torch symmetric memory) buffers of the multi-GPU bake: every rank's accumulators, atlas and
+    mask are addressable from every GPU of the node over NVLink / NVSwitch, which is what
+    wr_uv_reduce_finalize_p2p reads and writes.  Creating one is a collective call."""
+
+    def __init__(self, uv_h: int, uv_w: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > _native.MAX_P2P_RANKS:
+            raise RuntimeError(f"at most {_native.MAX_P2P_RANKS} ranks share a peer-memory bake")
+        T = uv_h * uv_w
+        if T % 4 != 0:
+            raise RuntimeError("peer-memory bake needs uv_h * uv_w to be a multiple of 4")
+        self.uv_h, self.uv_w, self.T = uv_h, uv_w, T
+        self._off_accum, self._off_attr, self._off_valid = 0, 20 * T, 32 * T  # byte offsets, all 16-byte aligned
+        self.buf = symm_mem.empty(33 * T, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.accum = self.buf[0:20 * T].view(torch.float32).view(uv_h, uv_w, 5)
+        self.attr = self.buf[20 * T:32 * T].view(torch.float32).view(uv_h, uv_w, 3)
+        self.valid = self.buf[32 * T:33 * T].view(uv_h, uv_w)
+
+    def barrier(self, channel: int) -> None:
+        self.hdl.barrier(channel=channel)  # device-side, ordered on the current stream
+
+    def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor]):
+        a = _native.P2PReduceArgs()
+        for r in range(self.world):
+            a.accum[r] = self.base_ptrs[r] + self._off_accum
+            a.out_attr[r] = self.base_ptrs[r] + self._off_attr
+            a.out_valid[r] = self.base_ptrs[r] + self._off_valid
+        old = None
+        if old_attr is not None:
+            old = old_attr.to(torch.float32).contiguous()
+            a.old_attr = _native.ptr(old)
+        a.world, a.rank, a.Hu, a.Wu = self.world, self.rank, self.uv_h, self.uv_w
+        self.barrier(0)  # every rank's accumulators are complete
+        c = ctx.ctx
+        c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()),
+                "wr_uv_reduce_finalize_p2p")
+        self.barrier(1)  # every rank's share of this atlas has landed
+        del old
+        return self.attr, self.valid.view(torch.bool)
+
+
+_P2P_WORKSPACES: Dict[tuple, "P2PBakeWorkspace"] = {}
+_P2P_DISABLED = False
+
+
+def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group) -> Optional["P2PBakeWorkspace"]:
+    """Workspace for (size, group), created on first use; None when peer memory is not usable (then NCCL)."""
+    global _P2P_DISABLED
+    if _P2P_DISABLED or not (dist.is_available() and dist.is_initialized()):
+        return None
+    if dist.get_backend(group) != "nccl" or dist.get_world_size(group) < 2 or (uv_h * uv_w) % 4 != 0:
+        return None
+    key = (uv_h, uv_w, device.index, id(group))
+    ws = _P2P_WORKSPACES.get(key)
+    if ws is None:
+        try:
+            ws = P2PBakeWorkspace(uv_h, uv_w, device, group)
+        except Exception as e:  # all ranks take the same branch: rendezvous is collective and fails everywhere
+            warnings.warn(f"peer-memory bake unavailable ({type(e).__name__}: {e}); using NCCL all_reduce")
+            _P2P_DISABLED = True
+            return None
+        _P2P_WORKSPACES[key] = ws
+    return ws
+
+
 def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_size: int, *, view_masks_local=None,
                  aoi_cos_valid_threshold: float = 0.3, depth_grad_dilation: int = 5,
                  depth_grad_threshold: Optional[float] = 0.1, uv_exp_blend_alpha: float = 6.0,
-                 uv_exp_blend_view_weight_local=None, group=None):
+                 uv_exp_blend_view_weight_local=None, group=None, exchange: str = "auto"):
     """Config E: this rank holds `cam_local` / `images_local` (its share of the views, possibly none);
-    the mesh is replicated.  Returns (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on all ranks."""
+    the mesh is replicated.  Returns (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on all ranks.
+
+    exchange: "p2p"  -- one fused kernel over NVLink peer memory (reduce-scatter + finalise + all-gather);
+              "nccl" -- all_reduce(SUM) of the accumulators, then wr_uv_finalize on every rank;
+              "auto" -- p2p when symmetric memory is available for the group, else nccl.
+    With "p2p" / "auto" the returned tensors are views of the workspace: valid until the next bake of that size."""
     from .uv import fused_unproject, fused_view_maps, uv_finalize, uv_precompute
+    if exchange not in ("auto", "p2p", "nccl"):
+        raise ValueError(f"exchange={exchange!r}")
     pre = uv_precompute(ctx, mesh, uv_size, uv_size)
+    ws = _p2p_workspace(uv_size, uv_size, ctx.device, group) if exchange != "nccl" else None
+    if exchange == "p2p" and ws is None:
+        raise RuntimeError("exchange='p2p' requested but peer memory is not available for this process group")
     n_local = cam_local.mvp_mtx.shape[0]
+    accum = ws.accum if ws is not None else None
     if n_local > 0:
         H, W = int(images_local.shape[1]), int(images_local.shape[2])
         _, geo, att = fused_view_maps(ctx, mesh, cam_local, images_local, H, W, int(depth_grad_dilation))
         _, _, accum, _, _ = fused_unproject(
             ctx, pre, cam_local, H, W, geo, att, view_masks=view_masks_local, aoi_cos_thresh=aoi_cos_valid_threshold,
             depth_grad_thresh=depth_grad_threshold, alpha=uv_exp_blend_alpha,
-            view_weight=uv_exp_blend_view_weight_local, accumulate_only=True)
+            view_weight=uv_exp_blend_view_weight_local, accumulate_only=True, accum=accum, add_to_accum=False)
+    elif accum is not None:
+        accum.zero_()
     else:
         accum = torch.zeros((uv_size, uv_size, 5), dtype=torch.float32, device=ctx.device)
+    if ws is not None:
+        return ws.reduce_finalize(ctx, pre.uv_attr)
     all_reduce_accumulators(accum, group)
     return uv_finalize(ctx, accum, pre.uv_attr)

@@ -345,8 +345,9 @@ def fused_view_maps(ctx, mesh, cam, images, H, W, dilation):
 def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, geo, att, view_masks=None, *,
                     pos_error_eps=1e-3, aoi_cos_thresh=0.1, mask_thresh=0.9, depth_grad_thresh=None,
                     first_view_dominate=False, alpha=1.0, view_weight=None, want_per_view=False,
-                    accumulate_only=False, accum: Optional[torch.Tensor] = None):
-    """One wr_uv_unproject launch.  Returns (attr_blend, valid_any, accum, uv_depth_grad, uv_aoi_cos)."""
+                    accumulate_only=False, accum: Optional[torch.Tensor] = None, add_to_accum: bool = True):
+    """One wr_uv_unproject launch.  Returns (attr_blend, valid_any, accum, uv_depth_grad, uv_aoi_cos).
+    With accumulate_only, a given `accum` is added to (add_to_accum=True) or overwritten (False)."""
     dev = ctx.device
     uv_pos = _f32c(pre.uv_pos)
     uv_mask = pre.uv_mask.contiguous().view(torch.uint8)
@@ -380,7 +381,9 @@ def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, g
         if accum is None:
             accum = torch.empty((Hu, Wu, 5), dtype=torch.float32, device=dev)
         else:
-            a.accumulate = 1
+            if accum.shape != (Hu, Wu, 5) or accum.dtype != torch.float32 or not accum.is_contiguous():
+                raise ValueError("accum must be a contiguous float32 tensor of shape [Huv, Wuv, 5]")
+            a.accumulate = 1 if add_to_accum else 0
         a.accum = _native.ptr(accum)
     else:
         old = pre.uv_attr
