@@ -202,6 +202,12 @@ typedef struct wr_p2p_reduce_args {
     uint8_t *out_valid[WR_MAX_P2P_RANKS];
     const float *old_attr;    /* local [Hu,Wu,3] or NULL (same texture on every rank) */
     int world, rank, Hu, Wu;
+    /* Optional NVSwitch multicast mappings of the same three buffers (all NULL = peer pointers above are used):
+       the sum is then computed in the switch (multimem.ld_reduce) and the result broadcast by one store
+       (multimem.st).  The in-switch summation order is the hardware's. */
+    const float *mc_accum;
+    float *mc_attr;
+    uint8_t *mc_valid;
 } wr_p2p_reduce_args;
 int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *args, void *stream);
 

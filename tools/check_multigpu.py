@@ -67,8 +67,15 @@ for size in (1024, 2048, 4096):
         parallel.all_reduce_accumulators(t)
         return uv_finalize(ctx, t, old)
     def run_p2p():
-        return ws.reduce_finalize(ctx, old)
-    for name, fn in (("nccl", run_nccl), ("p2p", run_p2p)):
+        return ws.reduce_finalize(ctx, old, multicast=False)
+    def run_mc():
+        return ws.reduce_finalize(ctx, old, multicast=True)
+    modes = [("nccl", run_nccl), ("p2p", run_p2p)] + ([("mc", run_mc)] if ws.mc_ptr else [])
+    if ws.mc_ptr:
+        a1, m1 = run_p2p(); a1, m1 = a1.clone(), m1.clone()
+        a2, m2 = run_mc()
+        exch[(size, "mc_err")] = float((a1 - a2).abs().max()); exch[(size, "mc_mask")] = bool(torch.equal(m1, m2))
+    for name, fn in modes:
         for _ in range(3):
             fn()
         torch.cuda.synchronize(); dist.barrier()
@@ -107,6 +114,7 @@ if rank == 0:
           f"ranks_identical={same} meshes_rendered={int(n_local)} covered_texels={int(any_.sum())}")
     for size in (1024, 2048, 4096):
         print(f"exchange step atlas {size}^2: nccl all_reduce+finalize {exch[(size, 'nccl')]:.3f} ms, "
-              f"fused p2p kernel {exch[(size, 'p2p')]:.3f} ms")
+              f"fused p2p kernel {exch[(size, 'p2p')]:.3f} ms, fused multicast kernel "
+              f"{exch.get((size, 'mc'), float('nan')):.3f} ms (vs p2p: max abs {exch.get((size, 'mc_err'))}, mask equal {exch.get((size, 'mc_mask'))})")
     print("PASS" if int(flag) == 1 and int(n_local) == 4 else "FAIL")
 dist.destroy_process_group()

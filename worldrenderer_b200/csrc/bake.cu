@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(256) k_grid_sample(const float *map, int H, in
 
 // Fused reduce-scatter + finalise + all-gather of the bake accumulators over NVLink peer memory (multi-GPU
 // bake).  Every rank owns a contiguous range of 1024-texel blocks.  For its blocks it
-//   1. sums the [.,5] accumulators of ALL ranks with coalesced 16-byte loads straight from peer memory, in
-//      fixed rank order (so the result does not depend on which rank computes it),
+//   1. sums the [.,5] accumulators of ALL ranks with coalesced 16-byte loads straight from peer memory (each
+//      texel is summed by exactly one rank, in an order fixed by that rank),
 //   2. finalises in shared memory / registers (divide, valid-any, stitch with the old texture), and
 //   3. stores the finished texels into EVERY rank's atlas and mask (peer stores).
 // One kernel replaces NCCL all-reduce (2 x 20 B per texel over the wire) + finalize; wire traffic per texel
@@ -318,12 +318,24 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
         const long long t0 = blk * kP2PTexelsPerBlock;
         const long long nt = min((long long)kP2PTexelsPerBlock, ntex - t0);  // multiple of 4
         const int nchunks = (int)(nt * 5 / 4);
+        // per chunk: one 16-byte load from every rank in flight together, starting at the next rank so that the
+        // ranks do not all pull from rank 0 at the same moment.  The summation order (rank+1, rank+2, ...) is a
+        // fixed function of the owner of the texel, and only the owner computes it: results are reproducible
+        // and identical on every rank.
         for (int j = threadIdx.x; j < nchunks; j += blockDim.x) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < A.world; ++r) {
-                const float4 v = *(reinterpret_cast<const float4 *>(A.accum[r] + 5 * t0) + j);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            float4 v[WR_MAX_P2P_RANKS];
+#pragma unroll
+            for (int i = 0; i < WR_MAX_P2P_RANKS; ++i) {
+                if (i < A.world) {
+                    int r = A.rank + 1 + i;
+                    if (r >= A.world) r -= A.world;
+                    v[i] = *(reinterpret_cast<const float4 *>(A.accum[r] + 5 * t0) + j);
+                }
             }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < WR_MAX_P2P_RANKS; ++i)
+                if (i < A.world) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
             s_sum[j] = acc;
         }
         __syncthreads();
@@ -357,6 +369,85 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
                 d[2] = make_float4(res[8], res[9], res[10], res[11]);
                 *reinterpret_cast<uchar4 *>(A.out_valid[r] + t) = anyv;
             }
+        }
+        __syncthreads();
+    }
+}
+
+
+// Same exchange through the NVSwitch multicast window (NVLS): multimem.ld_reduce returns the sum of all ranks'
+// accumulators computed IN the switch (each rank pulls 20 B per owned texel instead of 20 B x world), and
+// multimem.st writes the finished texels to every rank with one store (13 B out per owned texel instead of
+// 13 B x world).
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f32x4(const float *mc_addr)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc_addr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_f32x4(float *mc_addr, float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float *mc_addr, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_uv_reduce_finalize_mc(wr_p2p_reduce_args A, long long ntex, long long blk_lo,
+                                                               long long blk_hi)
+{
+    __shared__ float4 s_sum[kP2PTexelsPerBlock * 5 / 4];
+    for (long long blk = blk_lo + blockIdx.x; blk < blk_hi; blk += gridDim.x) {
+        const long long t0 = blk * kP2PTexelsPerBlock;
+        const long long nt = min((long long)kP2PTexelsPerBlock, ntex - t0);
+        const int nchunks = (int)(nt * 5 / 4);
+        {   // all five 16-byte reductions of a thread are issued before the first result is consumed
+            float4 v[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int j = threadIdx.x + k * 256;
+                if (j < nchunks) v[k] = multimem_ld_reduce_add_f32x4(A.mc_accum + 5 * t0 + 4 * (long long)j);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int j = threadIdx.x + k * 256;
+                if (j < nchunks) s_sum[j] = v[k];
+            }
+        }
+        __syncthreads();
+        const int q = threadIdx.x;
+        if (4 * q < nt) {
+            const float *sf = reinterpret_cast<const float *>(s_sum) + 20 * q;
+            float res[12];
+            uint32_t anyw = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float *a = sf + 5 * k;
+                const float den = fmaxf(a[3], 1e-5f);
+                const bool any = a[4] > 0.5f;
+                const float va = any ? 1.0f : 0.0f;
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+                if (A.old_attr) {
+                    const float *op = A.old_attr + 3 * (t0 + 4 * q + k);
+                    o0 = op[0]; o1 = op[1]; o2 = op[2];
+                }
+                res[3 * k] = (a[0] / den) * va + o0 * (1.0f - va);
+                res[3 * k + 1] = (a[1] / den) * va + o1 * (1.0f - va);
+                res[3 * k + 2] = (a[2] / den) * va + o2 * (1.0f - va);
+                anyw |= (any ? 1u : 0u) << (8 * k);
+            }
+            const long long t = t0 + 4 * q;
+            float *d = A.mc_attr + 3 * t;
+            multimem_st_f32x4(d, make_float4(res[0], res[1], res[2], res[3]));
+            multimem_st_f32x4(d + 4, make_float4(res[4], res[5], res[6], res[7]));
+            multimem_st_f32x4(d + 8, make_float4(res[8], res[9], res[10], res[11]));
+            multimem_st_f32(reinterpret_cast<float *>(A.mc_valid + t), __uint_as_float(anyw));  // 4 mask bytes, bits preserved
         }
         __syncthreads();
     }
@@ -450,7 +541,8 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
         return WR_ERR_INVALID_ARGUMENT;
     const long long ntex = (long long)A.Hu * A.Wu;
     if (ntex % 4 != 0) return WR_ERR_UNSUPPORTED;
-    for (int r = 0; r < A.world; ++r) {
+    const bool multicast = A.mc_accum && A.mc_attr && A.mc_valid;
+    for (int r = 0; r < A.world && !multicast; ++r) {
         if (!A.accum[r] || !A.out_attr[r] || !A.out_valid[r]) return WR_ERR_INVALID_ARGUMENT;
         if ((reinterpret_cast<uintptr_t>(A.accum[r]) | reinterpret_cast<uintptr_t>(A.out_attr[r])) & 15u) return WR_ERR_INVALID_ARGUMENT;
         if (reinterpret_cast<uintptr_t>(A.out_valid[r]) & 3u) return WR_ERR_INVALID_ARGUMENT;
@@ -463,9 +555,15 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
     if (blk_hi > blk_lo) {
         const int grid = (int)min(blk_hi - blk_lo, (long long)ctx->sm_count * 8);
         wr_stage_begin(ctx);
-        wr_stage(ctx, stream, "k_uv_reduce_finalize_p2p");
-        k_uv_reduce_finalize_p2p<<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
-        WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_p2p");
+        if (multicast) {
+            wr_stage(ctx, stream, "k_uv_reduce_finalize_mc");
+            k_uv_reduce_finalize_mc<<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_mc");
+        } else {
+            wr_stage(ctx, stream, "k_uv_reduce_finalize_p2p");
+            k_uv_reduce_finalize_p2p<<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_p2p");
+        }
         wr_stage(ctx, stream, "end");
     }
     return WR_OK;

@@ -100,6 +100,10 @@ class P2PBakeWorkspace:
         self.buf = symm_mem.empty(33 * T, dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.base_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        try:  # NVSwitch multicast window over the same allocation (0 / absent when NVLS is not available)
+            self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        except Exception:
+            self.mc_ptr = 0
         self.accum = self.buf[0:20 * T].view(torch.float32).view(uv_h, uv_w, 5)
         self.attr = self.buf[20 * T:32 * T].view(torch.float32).view(uv_h, uv_w, 3)
         self.valid = self.buf[32 * T:33 * T].view(uv_h, uv_w)
@@ -107,8 +111,19 @@ class P2PBakeWorkspace:
     def barrier(self, channel: int) -> None:
         self.hdl.barrier(channel=channel)  # device-side, ordered on the current stream
 
-    def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor]):
+    def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor], multicast: Optional[bool] = None):
+        """multicast: True / False force the NVSwitch multicast (multimem) or the peer load / store kernel; None
+        picks multicast from 4 ranks up when the window exists (measured on 8 x B200, 4096^2 atlas: multicast
+        0.64 ms, peer 1.19 ms, NCCL all_reduce + finalize 1.09 ms; on 2 ranks peer 0.52 ms, multicast 0.79 ms)."""
         a = _native.P2PReduceArgs()
+        if multicast is None:
+            multicast = bool(self.mc_ptr) and self.world >= 4
+        if multicast and self.mc_ptr:
+            a.mc_accum = self.mc_ptr + self._off_accum
+            a.mc_attr = self.mc_ptr + self._off_attr
+            a.mc_valid = self.mc_ptr + self._off_valid
+        elif multicast:
+            raise RuntimeError("no multicast window for this workspace")
         for r in range(self.world):
             a.accum[r] = self.base_ptrs[r] + self._off_accum
             a.out_attr[r] = self.base_ptrs[r] + self._off_attr
