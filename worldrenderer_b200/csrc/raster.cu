@@ -78,6 +78,12 @@ __device__ __forceinline__ SnapVert load_sv(const SnapVert *sv, size_t i)
     int4 r = __ldg(reinterpret_cast<const int4 *>(sv) + i);
     return *reinterpret_cast<SnapVert *>(&r);
 }
+// per-view base + 32-bit vertex index: one IMAD.WIDE.U32 per gather instead of 64-bit multiply-add chains
+__device__ __forceinline__ SnapVert load_sv32(const SnapVert *view_base, unsigned i)
+{
+    int4 r = __ldg(reinterpret_cast<const int4 *>(view_base) + i);
+    return *reinterpret_cast<SnapVert *>(&r);
+}
 
 __device__ __forceinline__ void resolve_sample(unsigned long long *dst, float zw, uint32_t id)
 {
@@ -112,7 +118,7 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
     int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
     int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
     int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
-    unsigned long long *row = depth_view + (size_t)r0 * W;
+    unsigned row = (unsigned)r0 * (unsigned)W;  // pixel offsets fit 32 bits (H, W <= 8192)
 #pragma unroll 1
     for (int r = r0; r <= r1; ++r) {
         int e0 = e0r, e1 = e1r, e2 = e2r;
@@ -124,12 +130,12 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
                 const float b2 = (1.0f - b0) - b1;
                 float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
                 zw = zw + 0.0f;
-                if (zw >= -1.0f && zw <= 1.0f) resolve_sample(row + cc, zw, id);
+                if (zw >= -1.0f && zw <= 1.0f) resolve_sample(depth_view + (row + (unsigned)cc), zw, id);
             }
             e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
         }
         e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
-        row += W;
+        row += (unsigned)W;
     }
 }
 
@@ -147,13 +153,13 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x2 = 0, y2 = 0, c0 = 0, c1 = 0, r0 = 0, r1 = 0;
     float z0 = 0.f, z1 = 0.f, z2 = 0.f;
     unsigned long long *depth_view = P.depth + (size_t)b * H * W;
+    const SnapVert *svb = P.sv + (size_t)b * P.V;
 
     if (t < P.F) {
         const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
                   i2 = __ldg(P.tri + 3 * (size_t)t + 2);
         if ((unsigned)i0 < (unsigned)P.V && (unsigned)i1 < (unsigned)P.V && (unsigned)i2 < (unsigned)P.V) {
-            const size_t vb = (size_t)b * P.V;
-            const SnapVert a = load_sv(P.sv, vb + i0), c = load_sv(P.sv, vb + i1), d = load_sv(P.sv, vb + i2);
+            const SnapVert a = load_sv32(svb, (unsigned)i0), c = load_sv32(svb, (unsigned)i1), d = load_sv32(svb, (unsigned)i2);
             const uint32_t f_and = a.flags & c.flags & d.flags;
             if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0) {
                 if (!(f_and & WR_SV_OK)) {
@@ -185,6 +191,7 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
         }
     }
     // warp-aggregated queue append: medium from the front, large / slow from the back
+    if (__ballot_sync(0xFFFFFFFFu, push != 0) == 0) return;
 #pragma unroll
     for (int q = 1; q <= 2; ++q) {
         const unsigned m = __ballot_sync(0xFFFFFFFFu, push == q);
