@@ -104,6 +104,7 @@ typedef struct wr_render_args {
     const float *v_nrm;       /* [Vn,3] or NULL (no normal map) */
     const int32_t *tri_nrm;   /* [F,3] indices into v_nrm (the stitched faces, render.py:275); NULL = tri */
     int Vn;
+    const float *v_tang;      /* [Vn,3] or NULL (no tangent map); indexed by tri_nrm like v_nrm (render.py:281) */
     const float *v_tex;       /* [Vt,2] or NULL (no attr map) */
     const int32_t *tri_tex;   /* [F,3] */
     int Vt;
@@ -120,12 +121,14 @@ typedef struct wr_render_args {
     int depth_clamp;          /* simple: clamp to [0,1] */
     float depth_bg;           /* value written where the mask is false (ignored for WR_DEPTH_NONE) */
     float normal_bg[3];
+    float tangent_bg[3];
     float attr_bg;
     /* outputs, each may be NULL */
     uint8_t *out_mask;        /* [B,H,W] 0/1 */
     float *out_pos;           /* [B,H,W,3] */
     float *out_depth;         /* [B,H,W] */
     float *out_normal;        /* [B,H,W,3] */
+    float *out_tangent;       /* [B,H,W,3] normalised interpolated tangents (render.py:280-284) */
     float *out_attr;          /* [B,H,W,TC] */
     int32_t *out_tri_id;      /* [B,H,W] */
     float *out_rast;          /* [B,H,W,4] nvdiffrast layout */

@@ -225,3 +225,24 @@ def test_config_b_full_size_bit_exact_ids_against_oracle(wr_ctx):
     np.testing.assert_allclose(raw["normal"].cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(raw["depth"].cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
     assert ref["mask"].sum() > 700_000
+
+
+def test_render_tangent_fused(wr_ctx):
+    """render_tangent=True (render.py:280-284): interpolated + normalised v_tang, against the operator form."""
+    v, f = cases.icosphere_mesh(6)
+    mesh = make_mesh(v, f, wr_ctx.device, with_uv=True)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    out = wr.render(wr_ctx, mesh, cam, 96, 96, render_attr=False, render_tangent=True, tangent_background=0.25)
+    raw = render_geometry_raw(wr_ctx, mesh, cam, 96, 96, want_rast=True)
+    tang, _ = wr_ctx.interpolate(mesh.v_tang[None], raw["rast"], mesh.t_pos_idx)
+    tang = torch.nn.functional.normalize(tang, dim=-1, p=2)
+    tang[~raw["mask"]] = 0.25
+    assert out.tangent.shape == (6, 96, 96, 3)
+    torch.testing.assert_close(out.tangent, tang, rtol=1e-5, atol=1e-6)
+    # and the interpolation itself against the oracle
+    from oracle import shim
+    ref = shim.interpolate(mesh.v_tang.cpu().numpy()[None], raw["rast"].cpu().numpy(), f)
+    ln = np.sqrt((ref * ref).sum(-1, keepdims=True))
+    ref = ref / np.maximum(ln, 1e-12)
+    m = raw["mask"].cpu().numpy()
+    np.testing.assert_allclose(out.tangent.cpu().numpy()[m], ref[m], rtol=1e-5, atol=1e-6)

@@ -32,6 +32,7 @@ class RenderArgs(ctypes.Structure):
     _fields_ = [
         ("v_pos", ctypes.c_void_p), ("tri", ctypes.c_void_p), ("V", ctypes.c_int), ("F", ctypes.c_int),
         ("v_nrm", ctypes.c_void_p), ("tri_nrm", ctypes.c_void_p), ("Vn", ctypes.c_int),
+        ("v_tang", ctypes.c_void_p),
         ("v_tex", ctypes.c_void_p), ("tri_tex", ctypes.c_void_p), ("Vt", ctypes.c_int),
         ("texture", ctypes.c_void_p), ("TH", ctypes.c_int), ("TW", ctypes.c_int), ("TC", ctypes.c_int),
         ("tex_filter", ctypes.c_int),
@@ -39,9 +40,9 @@ class RenderArgs(ctypes.Structure):
         ("B", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
         ("depth_mode", ctypes.c_int), ("depth_p0", ctypes.c_float), ("depth_p1", ctypes.c_float),
         ("depth_clamp", ctypes.c_int), ("depth_bg", ctypes.c_float),
-        ("normal_bg", ctypes.c_float * 3), ("attr_bg", ctypes.c_float),
+        ("normal_bg", ctypes.c_float * 3), ("tangent_bg", ctypes.c_float * 3), ("attr_bg", ctypes.c_float),
         ("out_mask", ctypes.c_void_p), ("out_pos", ctypes.c_void_p), ("out_depth", ctypes.c_void_p),
-        ("out_normal", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_tri_id", ctypes.c_void_p),
+        ("out_normal", ctypes.c_void_p), ("out_tangent", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_tri_id", ctypes.c_void_p),
         ("out_rast", ctypes.c_void_p),
     ]
 

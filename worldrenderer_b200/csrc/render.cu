@@ -30,6 +30,7 @@ struct ShadeParams {
 struct PixelGeo {
     float px, py, pz;   // world position (zeros on background)
     float nx, ny, nz;   // normalised normal (background value on background)
+    float tx, ty, tz;   // normalised tangent (generic instantiation only)
     float u, v, w;      // clamped barycentrics, w = (1 - u) - v
     float zw;           // clamped z/w (only when requested)
 };
@@ -56,7 +57,7 @@ __device__ __forceinline__ float apply_simple(float d, float scale, float offset
 
 // Everything render() derives for a covered pixel (c, r) won by triangle `id`.  m = mvp of the view.
 __device__ __forceinline__ void shade_covered(const wr_render_args &A, const float *m, int id, int c, int r,
-                                              bool want_normal, bool want_zw, PixelGeo &g)
+                                              bool want_normal, bool want_zw, bool want_tangent, PixelGeo &g)
 {
     const int W = A.W, H = A.H;
     const int i0 = __ldg(A.tri + 3 * (size_t)id), i1 = __ldg(A.tri + 3 * (size_t)id + 1),
@@ -125,6 +126,23 @@ __device__ __forceinline__ void shade_covered(const wr_render_args &A, const flo
         const float dn = fmaxf(ln, 1e-12f);
         g.nx = ix / dn; g.ny = iy / dn; g.nz = iz / dn;
     }
+    if (want_tangent) {  // render.py:280-284: same faces as the normals (stitched_t_pos_idx)
+        int j0 = i0, j1 = i1, j2 = i2;
+        if (A.tri_nrm) {
+            j0 = __ldg(A.tri_nrm + 3 * (size_t)id); j1 = __ldg(A.tri_nrm + 3 * (size_t)id + 1);
+            j2 = __ldg(A.tri_nrm + 3 * (size_t)id + 2);
+        }
+        float ix = 0.f, iy = 0.f, iz = 0.f;
+        if ((unsigned)j0 < (unsigned)A.Vn && (unsigned)j1 < (unsigned)A.Vn && (unsigned)j2 < (unsigned)A.Vn) {
+            const float *t0 = A.v_tang + 3 * (size_t)j0, *t1 = A.v_tang + 3 * (size_t)j1, *t2 = A.v_tang + 3 * (size_t)j2;
+            ix = ((__ldg(t0) * u) + (__ldg(t1) * v)) + (__ldg(t2) * w);
+            iy = ((__ldg(t0 + 1) * u) + (__ldg(t1 + 1) * v)) + (__ldg(t2 + 1) * w);
+            iz = ((__ldg(t0 + 2) * u) + (__ldg(t1 + 2) * v)) + (__ldg(t2 + 2) * w);
+        }
+        const float ln = sqrtf((ix * ix + iy * iy) + iz * iz);
+        const float dn = fmaxf(ln, 1e-12f);
+        g.tx = ix / dn; g.ty = iy / dn; g.tz = iz / dn;
+    }
 }
 
 constexpr int kShadeRows = 4;  // rows per thread: four independent 8-byte loads in flight before any use
@@ -149,6 +167,7 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
     const bool has_id = kGeneric && A.out_tri_id != nullptr;
     const bool has_rast = kGeneric && A.out_rast != nullptr;
     const bool has_attr = kGeneric && A.out_attr != nullptr;
+    const bool has_tangent = kGeneric && A.out_tangent != nullptr;
 
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * kShadeRows;
@@ -194,15 +213,17 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
         PixelGeo g;
         g.px = g.py = g.pz = 0.f;
         g.nx = nbx; g.ny = nby; g.nz = nbz;
+        g.tx = A.tangent_bg[0]; g.ty = A.tangent_bg[1]; g.tz = A.tangent_bg[2];
         g.u = g.v = g.w = 0.f; g.zw = 0.f;
         if (covered) {
             P.packed[o] = WR_EMPTY_PIXEL;  // self-cleaning
             id = (int)(uint32_t)(pk[k] & 0xFFFFFFFFull);
-            shade_covered(A, m, id, c, r, has_normal, has_rast, g);
+            shade_covered(A, m, id, c, r, has_normal, has_rast, has_tangent, g);
         }
         if (has_mask) P.mask[o] = covered ? 1 : 0;
         if (has_pos) { float *d = A.out_pos + 3 * o; d[0] = g.px; d[1] = g.py; d[2] = g.pz; }
         if (has_normal) { float *d = A.out_normal + 3 * o; d[0] = g.nx; d[1] = g.ny; d[2] = g.nz; }
+        if (has_tangent) { float *d = A.out_tangent + 3 * o; d[0] = g.tx; d[1] = g.ty; d[2] = g.tz; }
         if (has_id) A.out_tri_id[o] = id;
         if (has_rast)
             reinterpret_cast<float4 *>(A.out_rast)[o] =
@@ -340,6 +361,7 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     if (!A.mvp || (A.V > 0 && !A.v_pos) || (A.F > 0 && !A.tri)) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_depth && !A.w2c) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_normal && !A.v_nrm) return WR_ERR_INVALID_ARGUMENT;
+    if (A.out_tangent && !A.v_tang) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_attr && (!A.v_tex || !A.tri_tex || !A.texture || A.TH <= 0 || A.TW <= 0 || A.TC <= 0)) return WR_ERR_INVALID_ARGUMENT;
     if (A.depth_mode < WR_DEPTH_NONE || A.depth_mode > WR_DEPTH_SIMPLE) return WR_ERR_INVALID_ARGUMENT;
     if (A.tex_filter < 0 || A.tex_filter > 1) return WR_ERR_UNSUPPORTED;
@@ -366,7 +388,8 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     wr_stage(ctx, stream, "k_shade");
     {
         const dim3 grid(wr_div_up(A.W, 128), wr_div_up(A.H, kShadeRows), A.B);
-        const bool plain = P.mask && A.out_pos && A.out_normal && A.out_depth && !A.out_tri_id && !A.out_rast && !A.out_attr;
+        const bool plain = P.mask && A.out_pos && A.out_normal && A.out_depth && !A.out_tri_id && !A.out_rast &&
+                           !A.out_attr && !A.out_tangent;
         if (plain && two_pass) k_shade<kOutsRenderDefault><<<grid, 128, 0, stream>>>(P);
         else if (plain) k_shade<kOutsBakeView><<<grid, 128, 0, stream>>>(P);
         else k_shade<-1><<<grid, 128, 0, stream>>>(P);

@@ -256,7 +256,8 @@ def _background_triplet(value, what: str):
 
 def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: Camera, height: int, width: int, *,
                         want_pos=True, want_depth=True, want_normal=True, want_attr=False, want_tri_id=False,
-                        want_rast=False, depth_normalization_strategy=None, normal_background=0.0,
+                        want_rast=False, want_tangent=False, tangent_background=0.0,
+                        depth_normalization_strategy=None, normal_background=0.0,
                         attr_background=0.5, texture_override=None, texture_filter_mode="linear"):
     """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool)."""
     dev = ctx.device
@@ -300,6 +301,24 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         a.normal_bg = (ctypes.c_float * 3)(*nbg)
         out["normal"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
         a.out_normal = _native.ptr(out["normal"])
+    tbg_tensor = None
+    if want_tangent:
+        v_tang = _f32c(mesh.v_tang)
+        tri_n = mesh.index_i32("stitched_t_pos_idx")
+        v_nrm_for_count = _f32c(mesh.v_nrm)
+        if v_tang.shape != v_nrm_for_count.shape:
+            raise ValueError("v_tang must have one row per (stitched) vertex, like v_nrm")
+        ctx._check_device(v_tang, tri_n)
+        keep += [v_tang, tri_n]
+        same_faces = mesh._stitched_t_pos_idx is None or mesh._stitched_t_pos_idx is mesh.t_pos_idx
+        a.v_tang, a.Vn = _native.ptr(v_tang), v_tang.shape[0]
+        a.tri_nrm = None if same_faces else _native.ptr(tri_n)
+        tbg = _background_triplet(tangent_background, "tangent_background")
+        if tbg is None:
+            tbg_tensor, tbg = tangent_background, [0.0, 0.0, 0.0]
+        a.tangent_bg = (ctypes.c_float * 3)(*tbg)
+        out["tangent"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        a.out_tangent = _native.ptr(out["tangent"])
     abg_tensor = None
     if want_attr:
         tex = texture_override if texture_override is not None else mesh.texture
@@ -333,6 +352,8 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
     mask_bool = out["mask"].view(torch.bool)
     if post is not None:
         out["depth"] = post(out["depth"], mask_bool)
+    if tbg_tensor is not None:
+        out["tangent"][~mask_bool] = tbg_tensor.to(out["tangent"])
     if nbg_tensor is not None:  # tensor-valued background, torch indexing like the reference (render.py:277)
         out["normal"][~mask_bool] = nbg_tensor.to(out["normal"])
     if abg_tensor is not None:
@@ -363,18 +384,13 @@ def render(
     """Same signature and outputs as the reference render() (render.py:220-286)."""
     if antialias_attr:
         raise NotImplementedError("antialias_attr=True (dr.antialias) is outside the geometry path")
-    need_rast = bool(render_tangent)
     raw = render_geometry_raw(
         ctx, mesh, cam, height, width, want_pos=True, want_depth=render_depth, want_normal=render_normal,
-        want_attr=render_attr, want_rast=need_rast, depth_normalization_strategy=depth_normalization_strategy,
+        want_attr=render_attr, want_tangent=render_tangent, tangent_background=tangent_background,
+        depth_normalization_strategy=depth_normalization_strategy,
         normal_background=normal_background, attr_background=attr_background, texture_override=texture_override,
         texture_filter_mode=texture_filter_mode)
     out = RenderOutput(mask=raw["mask"], pos=raw["pos"], depth=raw.get("depth"), attr=raw.get("attr"),
                        normal=raw.get("normal"))
-    if render_tangent:
-        # render.py:280-284; tangents are a "next" row (SURVEY 8f-4): operator path + torch post-processing
-        tang, _ = ctx.interpolate(mesh.v_tang[None], raw["rast"], mesh.index_i32("stitched_t_pos_idx"))
-        tang = F.normalize(tang, dim=-1, p=2)
-        tang[~raw["mask"]] = tangent_background
-        out.tangent = tang
+    out.tangent = raw.get("tangent")
     return out
