@@ -129,6 +129,7 @@ typedef struct wr_render_args {
     float *out_depth;         /* [B,H,W] */
     float *out_normal;        /* [B,H,W,3] */
     float *out_tangent;       /* [B,H,W,3] normalised interpolated tangents (render.py:280-284) */
+    float *out_geo;           /* [B,H,W,4] bake view map (pos.xyz, aoi_cos), aoi_cos as in uv.py:108-119; needs v_nrm, w2c */
     float *out_attr;          /* [B,H,W,TC] */
     int32_t *out_tri_id;      /* [B,H,W] */
     float *out_rast;          /* [B,H,W,4] nvdiffrast layout */

@@ -42,7 +42,7 @@ class RenderArgs(ctypes.Structure):
         ("depth_clamp", ctypes.c_int), ("depth_bg", ctypes.c_float),
         ("normal_bg", ctypes.c_float * 3), ("tangent_bg", ctypes.c_float * 3), ("attr_bg", ctypes.c_float),
         ("out_mask", ctypes.c_void_p), ("out_pos", ctypes.c_void_p), ("out_depth", ctypes.c_void_p),
-        ("out_normal", ctypes.c_void_p), ("out_tangent", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_tri_id", ctypes.c_void_p),
+        ("out_normal", ctypes.c_void_p), ("out_tangent", ctypes.c_void_p), ("out_geo", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_tri_id", ctypes.c_void_p),
         ("out_rast", ctypes.c_void_p),
     ]
 

@@ -13,13 +13,14 @@
 
 namespace {
 
-// View side of the bake in one pass.  A 32x8 output tile per block; the depth tile (halo pad+1, zeros
+// View side of the bake in one pass.  A 32x32 output tile per 256-thread block; the depth tile (halo pad+1, zeros
 // outside the image = conv2d zero padding), the Sobel magnitude (halo pad, -inf outside the image =
 // max_pool2d padding) and the row maxima live in shared memory, so a pixel costs ~3 global loads instead
 // of the 9 + d*d of the two-kernel form (measured 102 us -> see profiles/README.md on config C).
-constexpr int kPrepTW = 32, kPrepTH = 8;
+constexpr int kPrepTW = 32, kPrepTH = 32;  // output tile per block
+constexpr int kPrepBH = 8;                 // block = 32 x 8 threads, four output rows per thread
 
-__global__ void __launch_bounds__(kPrepTW * kPrepTH) k_view_prep(const float *normal, const uint8_t *mask,
+__global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *normal, const uint8_t *mask,
                                                                 const float *depth, const float *position,
                                                                 const float *w2c, const float *images, int H, int W,
                                                                 int dilation, float *aoi_out, float *depth_grad,
@@ -35,71 +36,85 @@ __global__ void __launch_bounds__(kPrepTW * kPrepTH) k_view_prep(const float *no
     float *s_r = s_g + gh * gw;                // [gh][kPrepTW] row maxima
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kPrepTW, y0 = blockIdx.y * kPrepTH;
-    const int tid = threadIdx.y * kPrepTW + threadIdx.x;
-    const int nthreads = kPrepTW * kPrepTH;
-    float dg = 0.0f;
     if (dilation > 0) {
         const float *dv = depth + (size_t)b * H * W;
-        for (int i = tid; i < dh * dw; i += nthreads) {
-            const int yy = y0 - hd + i / dw, xx = x0 - hd + i % dw;
-            s_d[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
-        }
-        __syncthreads();
-        for (int i = tid; i < gh * gw; i += nthreads) {
-            const int gy_ = i / gw, gx_ = i % gw;
-            const int yy = y0 - pad + gy_, xx = x0 - pad + gx_;
-            float g = -INFINITY;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-                const float *c = s_d + (gy_ + 1) * dw + (gx_ + 1);  // centre of the 3x3 window in the depth tile
-                const float s00 = c[-dw - 1], s01 = c[-dw], s02 = c[-dw + 1];
-                const float s10 = c[-1], s12 = c[1];
-                const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
-                const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
-                const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
-                g = sqrtf(gx * gx + gy * gy);
+        // 2-D strided loops (no integer division): rows by threadIdx.y, columns by threadIdx.x
+        for (int ry = threadIdx.y; ry < dh; ry += kPrepBH) {
+            const int yy = y0 - hd + ry;
+            const bool yin = yy >= 0 && yy < H;
+            for (int rx = threadIdx.x; rx < dw; rx += kPrepTW) {
+                const int xx = x0 - hd + rx;
+                s_d[ry * dw + rx] = (yin && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
             }
-            s_g[i] = g;
         }
         __syncthreads();
-        for (int i = tid; i < gh * kPrepTW; i += nthreads) {
-            const int ry = i / kPrepTW, rx = i % kPrepTW;
-            const float *row = s_g + ry * gw + rx;
+        for (int gy_ = threadIdx.y; gy_ < gh; gy_ += kPrepBH) {
+            const int yy = y0 - pad + gy_;
+            const bool yin = yy >= 0 && yy < H;
+            for (int gx_ = threadIdx.x; gx_ < gw; gx_ += kPrepTW) {
+                const int xx = x0 - pad + gx_;
+                float g = -INFINITY;
+                if (yin && xx >= 0 && xx < W) {
+                    const float *c = s_d + (gy_ + 1) * dw + (gx_ + 1);  // centre of the 3x3 window in the depth tile
+                    const float s00 = c[-dw - 1], s01 = c[-dw], s02 = c[-dw + 1];
+                    const float s10 = c[-1], s12 = c[1];
+                    const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
+                    const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
+                    const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
+                    g = sqrtf(gx * gx + gy * gy);
+                }
+                s_g[gy_ * gw + gx_] = g;
+            }
+        }
+        __syncthreads();
+        for (int ry = threadIdx.y; ry < gh; ry += kPrepBH) {  // row maxima: one output column per thread
+            const float *row = s_g + ry * gw + threadIdx.x;
             float m = row[0];
             for (int k = 1; k < dilation; ++k) m = fmaxf(m, row[k]);
-            s_r[i] = m;
+            s_r[ry * kPrepTW + threadIdx.x] = m;
         }
         __syncthreads();
-        const float *col = s_r + threadIdx.y * kPrepTW + threadIdx.x;
-        dg = col[0];
-        for (int k = 1; k < dilation; ++k) dg = fmaxf(dg, col[k * kPrepTW]);
     }
-    const int c = x0 + threadIdx.x, r = y0 + threadIdx.y;
-    if (c >= W || r >= H) return;
-    const size_t o = ((size_t)b * H + r) * W + c;
-    const float *n = normal + 3 * o;
-    const float nx = n[0], ny = n[1], nz = n[2];
-    float aoi;
-    if (mask[o]) {
-        const float *R = w2c + 16 * b;
-        const float x = (R[0] * nx + R[1] * ny) + R[2] * nz;
-        const float y = (R[4] * nx + R[5] * ny) + R[6] * nz;
-        const float z = (R[8] * nx + R[9] * ny) + R[10] * nz;
-        const float ln = sqrtf((x * x + y * y) + z * z);
-        aoi = z / fmaxf(ln, 1e-12f);
-    } else {
-        aoi = nz;  // uv.py:112: background keeps the render's normal (normal_background)
-    }
-    aoi = fminf(fmaxf(aoi, 0.0f), 1.0f);
-    if (aoi_out) aoi_out[o] = aoi;
-    if (dilation > 0 && depth_grad) depth_grad[o] = dg;
-    if (geo_map) {
-        const float *p = position + 3 * o;
-        reinterpret_cast<float4 *>(geo_map)[o] = make_float4(p[0], p[1], p[2], aoi);
-    }
-    if (attr_map) {
-        float rr = 0.f, gg = 0.f, bb = 0.f;
-        if (images) { const float *im = images + 3 * o; rr = im[0]; gg = im[1]; bb = im[2]; }
-        reinterpret_cast<float4 *>(attr_map)[o] = make_float4(rr, gg, bb, dg);
+    const int c = x0 + threadIdx.x;
+    if (c >= W) return;
+#pragma unroll
+    for (int j = 0; j < kPrepTH / kPrepBH; ++j) {
+        const int ty = threadIdx.y + j * kPrepBH;  // row inside the tile
+        const int r = y0 + ty;
+        if (r >= H) break;
+        const size_t o = ((size_t)b * H + r) * W + c;
+        float dg = 0.0f;
+        if (dilation > 0) {
+            const float *col = s_r + ty * kPrepTW + threadIdx.x;
+            dg = col[0];
+            for (int k = 1; k < dilation; ++k) dg = fmaxf(dg, col[k * kPrepTW]);
+            if (depth_grad) depth_grad[o] = dg;
+        }
+        if (attr_map) {
+            float ir = 0.f, ig = 0.f, ib = 0.f;
+            if (images) { const float *im = images + 3 * o; ir = __ldg(im); ig = __ldg(im + 1); ib = __ldg(im + 2); }
+            reinterpret_cast<float4 *>(attr_map)[o] = make_float4(ir, ig, ib, dg);
+        }
+        if (!normal) continue;  // geometry half already produced by wr_render (out_geo)
+        const float *n = normal + 3 * o;
+        const float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
+        float aoi;
+        if (__ldg(mask + o)) {
+            const float *R = w2c + 16 * b;
+            const float x = (R[0] * nx + R[1] * ny) + R[2] * nz;
+            const float y = (R[4] * nx + R[5] * ny) + R[6] * nz;
+            const float z = (R[8] * nx + R[9] * ny) + R[10] * nz;
+            const float ln = sqrtf((x * x + y * y) + z * z);
+            aoi = z / fmaxf(ln, 1e-12f);
+        } else {
+            aoi = nz;  // uv.py:112: background keeps the render's normal (normal_background)
+        }
+        aoi = fminf(fmaxf(aoi, 0.0f), 1.0f);
+        if (aoi_out) aoi_out[o] = aoi;
+        if (geo_map) {
+            const float *p = position + 3 * o;
+            reinterpret_cast<float4 *>(geo_map)[o] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), aoi);
+        }
     }
 }
 
@@ -127,23 +142,28 @@ __device__ __forceinline__ Bilinear make_bilinear(float gx, float gy, int W, int
     return t;
 }
 
+__device__ __forceinline__ void tap4(float4 &acc, const float4 v, float w)
+{
+    acc.x = acc.x + v.x * w; acc.y = acc.y + v.y * w; acc.z = acc.z + v.z * w; acc.w = acc.w + v.w * w;
+}
+
+// Taps are added in the order (0,0), (1,0), (0,1), (1,1); a tap outside the map adds nothing (zero padding).
 __device__ __forceinline__ float4 sample4(const float4 *map, const Bilinear &t, int W, int H)
 {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!t.ok) return acc;
+    if (t.x0 >= 0 && t.y0 >= 0 && t.x0 + 1 < W && t.y0 + 1 < H) {  // interior: one base offset, no per-tap tests
+        const float4 *p = map + ((unsigned)t.y0 * (unsigned)W + (unsigned)t.x0);
+        const float4 v00 = __ldg(p), v10 = __ldg(p + 1), v01 = __ldg(p + W), v11 = __ldg(p + W + 1);
+        tap4(acc, v00, t.w00); tap4(acc, v10, t.w10); tap4(acc, v01, t.w01); tap4(acc, v11, t.w11);
+        return acc;
+    }
     const int xs[4] = { t.x0, t.x0 + 1, t.x0, t.x0 + 1 };
     const int ys[4] = { t.y0, t.y0, t.y0 + 1, t.y0 + 1 };
     const float ws[4] = { t.w00, t.w10, t.w01, t.w11 };
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H) {
-            const float4 v = __ldg(map + (size_t)ys[k] * W + xs[k]);
-            acc.x = acc.x + v.x * ws[k];
-            acc.y = acc.y + v.y * ws[k];
-            acc.z = acc.z + v.z * ws[k];
-            acc.w = acc.w + v.w * ws[k];
-        }
-    }
+    for (int k = 0; k < 4; ++k)
+        if (xs[k] >= 0 && xs[k] < W && ys[k] >= 0 && ys[k] < H) tap4(acc, __ldg(map + (size_t)ys[k] * W + xs[k]), ws[k]);
     return acc;
 }
 
@@ -160,8 +180,10 @@ __device__ __forceinline__ float sample1(const float *map, const Bilinear &t, in
     return acc;
 }
 
-__global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A, int materialise)
+template <bool MATERIALISE>
+__global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
 {
+    constexpr bool materialise = MATERIALISE;
     extern __shared__ float s_cam[];  // [Nv,16] mvp, then [Nv] exponent
     for (int i = threadIdx.x; i < A.Nv * 16; i += blockDim.x) s_cam[i] = A.mvp[i];
     float *s_expo = s_cam + A.Nv * 16;
@@ -478,7 +500,12 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     if (!ctx || B < 0 || H <= 0 || W <= 0 || dilation < 0) return WR_ERR_INVALID_ARGUMENT;
     if (dilation > 0 && (dilation & 1) == 0) return WR_ERR_UNSUPPORTED;  // even max-pool changes the map size
     if (B == 0) return WR_OK;
-    if (!normal || !mask || !w2c || (dilation > 0 && !depth) || (geo_map && !position)) return WR_ERR_INVALID_ARGUMENT;
+    if (normal) {
+        if (!mask || !w2c || (geo_map && !position)) return WR_ERR_INVALID_ARGUMENT;
+    } else if (aoi_cos || geo_map) {
+        return WR_ERR_INVALID_ARGUMENT;
+    }
+    if (dilation > 0 && !depth) return WR_ERR_INVALID_ARGUMENT;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
@@ -486,11 +513,11 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     const size_t smem = sizeof(float) * ((size_t)(kPrepTH + 2 * hd) * (kPrepTW + 2 * hd) +
                                          (size_t)(kPrepTH + 2 * pad) * (kPrepTW + 2 * pad) +
                                          (size_t)(kPrepTH + 2 * pad) * kPrepTW);
-    if (smem > 48 * 1024) return WR_ERR_UNSUPPORTED;  // dilation > ~60
+    if (smem > 48 * 1024) return WR_ERR_UNSUPPORTED;  // dilation > ~29
     const dim3 grid(wr_div_up(W, kPrepTW), wr_div_up(H, kPrepTH), B);
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_view_prep");
-    k_view_prep<<<grid, dim3(kPrepTW, kPrepTH), dilation > 0 ? smem : 0, stream>>>(
+    k_view_prep<<<grid, dim3(kPrepTW, kPrepBH), dilation > 0 ? smem : 0, stream>>>(
         normal, mask, depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map);
     WR_CHECK_LAUNCH(ctx, "k_view_prep");
     wr_stage(ctx, stream, "end");
@@ -514,7 +541,8 @@ extern "C" int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void 
     const long long ntex = (long long)A.Hu * A.Wu;
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_uv_unproject");
-    k_uv_unproject<<<wr_div_up(ntex, 256), 256, smem, stream>>>(A, materialise);
+    if (materialise) k_uv_unproject<true><<<wr_div_up(ntex, 256), 256, smem, stream>>>(A);
+    else k_uv_unproject<false><<<wr_div_up(ntex, 256), 256, smem, stream>>>(A);
     WR_CHECK_LAUNCH(ctx, "k_uv_unproject");
     wr_stage(ctx, stream, "end");
     return WR_OK;

@@ -149,9 +149,10 @@ constexpr int kShadeRows = 4;  // rows per thread: four independent 8-byte loads
 
 // Output sets with their own instantiation (no per-pixel pointer tests, ~30% fewer issued instructions on
 // config B); every other combination runs the generic instantiation (OUTS < 0, runtime tests).
-constexpr int kOutNormal = 1, kOutDepth = 2, kOutTwoPass = 4;
+constexpr int kOutNormal = 1, kOutDepth = 2, kOutTwoPass = 4, kOutGeo = 8;
 constexpr int kOutsRenderDefault = kOutNormal | kOutDepth | kOutTwoPass;  // mask + pos + normal + min/max depth
-constexpr int kOutsBakeView = kOutNormal | kOutDepth;                     // mask + pos + normal + simple depth
+constexpr int kOutsSimpleDepth = kOutNormal | kOutDepth;                  // mask + pos + normal + simple depth
+constexpr int kOutsBakeView = kOutGeo | kOutDepth;                        // mask + (pos, aoi_cos) + simple depth
 
 // One column strip of kShadeRows pixels per thread.  grid = (ceil(W/128), ceil(H/kShadeRows), B), 128 threads.
 template <int OUTS>
@@ -160,8 +161,10 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
     const wr_render_args &A = P.a;
     constexpr bool kGeneric = OUTS < 0;
     const bool has_mask = kGeneric ? (P.mask != nullptr) : true;
-    const bool has_pos = kGeneric ? (A.out_pos != nullptr) : true;
+    const bool has_geo = kGeneric ? (A.out_geo != nullptr) : ((OUTS & kOutGeo) != 0);
+    const bool has_pos = kGeneric ? (A.out_pos != nullptr) : !has_geo;
     const bool has_normal = kGeneric ? (A.out_normal != nullptr) : ((OUTS & kOutNormal) != 0);
+    const bool need_normal = has_normal || has_geo;
     const bool has_depth = kGeneric ? (A.out_depth != nullptr) : ((OUTS & kOutDepth) != 0);
     const bool two_pass = kGeneric ? (has_depth && A.depth_mode != WR_DEPTH_SIMPLE) : ((OUTS & kOutTwoPass) != 0);
     const bool has_id = kGeneric && A.out_tri_id != nullptr;
@@ -202,6 +205,11 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
         wz0 = __ldg(m2); wz1 = __ldg(m2 + 1); wz2 = __ldg(m2 + 2); wz3 = __ldg(m2 + 3);
     }
     const float nbx = A.normal_bg[0], nby = A.normal_bg[1], nbz = A.normal_bg[2];
+    float rot[9];
+    if (has_geo) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) rot[j] = __ldg(A.w2c + 16 * b + 4 * (j / 3) + (j % 3));  // R = w2c[:3,:3]
+    }
     float lo = INFINITY, hi = -INFINITY;
 
 #pragma unroll 1
@@ -218,9 +226,23 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
         if (covered) {
             P.packed[o] = WR_EMPTY_PIXEL;  // self-cleaning
             id = (int)(uint32_t)(pk[k] & 0xFFFFFFFFull);
-            shade_covered(A, m, id, c, r, has_normal, has_rast, has_tangent, g);
+            shade_covered(A, m, id, c, r, need_normal, has_rast, has_tangent, g);
         }
         if (has_mask) P.mask[o] = covered ? 1 : 0;
+        if (has_geo) {
+            // uv.py:108-119: camera-space normal, re-normalised, z clamped to [0,1]; background keeps the
+            // (un-rotated) background normal
+            float aoi = g.nz;
+            if (covered) {
+                const float x = (rot[0] * g.nx + rot[1] * g.ny) + rot[2] * g.nz;
+                const float y = (rot[3] * g.nx + rot[4] * g.ny) + rot[5] * g.nz;
+                const float z = (rot[6] * g.nx + rot[7] * g.ny) + rot[8] * g.nz;
+                const float ln = sqrtf((x * x + y * y) + z * z);
+                aoi = z / fmaxf(ln, 1e-12f);
+            }
+            aoi = fminf(fmaxf(aoi, 0.0f), 1.0f);
+            reinterpret_cast<float4 *>(A.out_geo)[o] = make_float4(g.px, g.py, g.pz, aoi);
+        }
         if (has_pos) { float *d = A.out_pos + 3 * o; d[0] = g.px; d[1] = g.py; d[2] = g.pz; }
         if (has_normal) { float *d = A.out_normal + 3 * o; d[0] = g.nx; d[1] = g.ny; d[2] = g.nz; }
         if (has_tangent) { float *d = A.out_tangent + 3 * o; d[0] = g.tx; d[1] = g.ty; d[2] = g.tz; }
@@ -361,6 +383,7 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     if (!A.mvp || (A.V > 0 && !A.v_pos) || (A.F > 0 && !A.tri)) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_depth && !A.w2c) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_normal && !A.v_nrm) return WR_ERR_INVALID_ARGUMENT;
+    if (A.out_geo && (!A.v_nrm || !A.w2c)) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_tangent && !A.v_tang) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_attr && (!A.v_tex || !A.tri_tex || !A.texture || A.TH <= 0 || A.TW <= 0 || A.TC <= 0)) return WR_ERR_INVALID_ARGUMENT;
     if (A.depth_mode < WR_DEPTH_NONE || A.depth_mode > WR_DEPTH_SIMPLE) return WR_ERR_INVALID_ARGUMENT;
@@ -388,10 +411,12 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     wr_stage(ctx, stream, "k_shade");
     {
         const dim3 grid(wr_div_up(A.W, 128), wr_div_up(A.H, kShadeRows), A.B);
-        const bool plain = P.mask && A.out_pos && A.out_normal && A.out_depth && !A.out_tri_id && !A.out_rast &&
-                           !A.out_attr && !A.out_tangent;
+        const bool extras = A.out_tri_id || A.out_rast || A.out_attr || A.out_tangent;
+        const bool plain = P.mask && A.out_pos && A.out_normal && A.out_depth && !A.out_geo && !extras;
+        const bool bake = P.mask && A.out_geo && A.out_depth && !two_pass && !A.out_pos && !A.out_normal && !extras;
         if (plain && two_pass) k_shade<kOutsRenderDefault><<<grid, 128, 0, stream>>>(P);
-        else if (plain) k_shade<kOutsBakeView><<<grid, 128, 0, stream>>>(P);
+        else if (plain) k_shade<kOutsSimpleDepth><<<grid, 128, 0, stream>>>(P);
+        else if (bake) k_shade<kOutsBakeView><<<grid, 128, 0, stream>>>(P);
         else k_shade<-1><<<grid, 128, 0, stream>>>(P);
     }
     WR_CHECK_LAUNCH(ctx, "k_shade");

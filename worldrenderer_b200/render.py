@@ -256,7 +256,7 @@ def _background_triplet(value, what: str):
 
 def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: Camera, height: int, width: int, *,
                         want_pos=True, want_depth=True, want_normal=True, want_attr=False, want_tri_id=False,
-                        want_rast=False, want_tangent=False, tangent_background=0.0,
+                        want_rast=False, want_tangent=False, tangent_background=0.0, want_geo=False,
                         depth_normalization_strategy=None, normal_background=0.0,
                         attr_background=0.5, texture_override=None, texture_filter_mode="linear"):
     """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool)."""
@@ -283,6 +283,18 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         a.depth_mode, a.depth_p0, a.depth_p1, a.depth_clamp, a.depth_bg = mode, p0, p1, clamp, bg
         out["depth"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         a.out_depth = _native.ptr(out["depth"])
+    if want_geo:  # bake view map (pos.xyz, aoi_cos): needs the vertex normals but writes no normal map
+        v_nrm = _f32c(mesh.v_nrm)
+        tri_n = mesh.index_i32("stitched_t_pos_idx")
+        ctx._check_device(v_nrm, tri_n)
+        keep += [v_nrm, tri_n]
+        same_faces = mesh._stitched_t_pos_idx is None or mesh._stitched_t_pos_idx is mesh.t_pos_idx
+        a.v_nrm, a.Vn = _native.ptr(v_nrm), v_nrm.shape[0]
+        a.tri_nrm = None if same_faces else _native.ptr(tri_n)
+        nbg = _background_triplet(normal_background, "normal_background") or [0.0, 0.0, 0.0]
+        a.normal_bg = (ctypes.c_float * 3)(*nbg)
+        out["geo"] = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        a.out_geo = _native.ptr(out["geo"])
     nbg_tensor = None
     if want_normal:
         v_nrm = _f32c(mesh.v_nrm)

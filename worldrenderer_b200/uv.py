@@ -337,9 +337,22 @@ class FusedBakeOutput:
 
 
 def fused_view_maps(ctx, mesh, cam, images, H, W, dilation):
-    """View pass of the fused bake: returns (view_mask bool [Nv,H,W], geo_map, attr_map)."""
-    raw, _, _, geo, att = _view_pass(ctx, mesh, cam, H, W, dilation, images=images, want_planes=False)
-    return raw["mask"], geo, att
+    """View pass of the fused bake: returns (view_mask bool [Nv,H,W], geo_map, attr_map).  The shading kernel
+    writes the packed (pos, aoi_cos) map directly (no position / normal maps in HBM); wr_view_prep then only
+    adds the depth gradient and packs (rgb, depth_grad)."""
+    dev = ctx.device
+    raw = render_geometry_raw(ctx, mesh, cam, H, W, want_pos=False, want_depth=True, want_normal=False, want_geo=True,
+                              depth_normalization_strategy=SimpleNormalization(**_BAKE_DEPTH))
+    B = raw["geo"].shape[0]
+    images = _f32c(images)
+    if images.shape != (B, H, W, 3):
+        raise ValueError(f"images must have shape {(B, H, W, 3)}, got {tuple(images.shape)}")
+    att = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+    c = ctx.ctx
+    status = _native.lib().wr_view_prep(c.handle, None, None, _native.ptr(raw["depth"]), None, None, _native.ptr(images),
+                                        B, H, W, int(dilation), None, None, None, _native.ptr(att), c.stream())
+    c.check(status, "wr_view_prep")
+    return raw["mask"], raw["geo"], att
 
 
 def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, geo, att, view_masks=None, *,
