@@ -69,6 +69,21 @@ def near_crossing_scene(seed: int = 5, n_tri: int = 200):
     return pos, tri
 
 
+def guard_band_scene(seed: int = 13, n_tri: int = 60):
+    """Triangles with vertices far outside the viewport (|x|, |y| up to 1e5 w): the snap range is exceeded, so
+    they take the geometric clip against the +-16 w guard planes."""
+    rng = np.random.default_rng(seed)
+    V = 3 * n_tri
+    pos = np.empty((1, V, 4), f32)
+    mag = 10.0 ** rng.uniform(0, 5, (V, 2))
+    pos[0, :, :2] = rng.choice([-1.0, 1.0], (V, 2)) * mag * rng.uniform(0.0, 1.0, (V, 2))
+    pos[0, :, 2] = rng.uniform(-0.9, 0.9, V)
+    pos[0, :, 3] = 1.0
+    pos[0, ::3, :2] = rng.uniform(-1, 1, (n_tri, 2))  # one vertex of every triangle inside the viewport
+    tri = np.arange(V, dtype=np.int32).reshape(-1, 3)
+    return pos, tri
+
+
 def big_and_small_mix(seed: int = 9):
     """A few screen-filling triangles + many tiny ones + off-screen ones + degenerate / bad-index faces."""
     rng = np.random.default_rng(seed)

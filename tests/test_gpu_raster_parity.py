@@ -84,6 +84,13 @@ def test_near_plane_and_negative_w(wr_ctx):
     _check(wr_ctx, pos, tri, (200, 320))
 
 
+def test_guard_band_clipping(wr_ctx):
+    pos, tri = cases.guard_band_scene()
+    for res in [(128, 128), (600, 800)]:
+        rast, ids, _ = _check(wr_ctx, pos, tri, res)
+        assert (ids >= 0).mean() > 0.3
+
+
 def test_big_small_degenerate_mix(wr_ctx):
     pos, tri = cases.big_and_small_mix()
     for res in [(300, 300), (1024, 1024)]:

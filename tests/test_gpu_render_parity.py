@@ -246,3 +246,27 @@ def test_render_tangent_fused(wr_ctx):
     ref = ref / np.maximum(ln, 1e-12)
     m = raw["mask"].cpu().numpy()
     np.testing.assert_allclose(out.tangent.cpu().numpy()[m], ref[m], rtol=1e-5, atol=1e-6)
+
+
+def test_many_views_small_resolution_and_single_view(wr_ctx):
+    """SmartPainter-style batch (smart_paint.py:102-111): many perspective views of a small mesh at low resolution."""
+    v, f = cases.icosphere_mesh(5)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    n = 36
+    cam = wr.get_camera(elevation_deg=list(np.linspace(-60, 60, n)), distance=[1.6] * n, fovy_deg=[45.0] * n,
+                        azimuth_deg=list(np.linspace(0, 350, n)), device=str(wr_ctx.device))
+    out = wr.render(wr_ctx, mesh, cam, 40, 56, render_attr=False)
+    ref = _oracle(mesh, cam, 40, 56, DepthSpec("controlnet"))
+    _compare(out, ref)
+    one = wr.render(wr_ctx, mesh, cam[17], 40, 56, render_attr=False)
+    assert torch.equal(one.mask[0], out.mask[17]) and torch.equal(one.normal[0], out.normal[17])
+
+
+def test_empty_mesh_renders_background(wr_ctx):
+    mesh = wr.TexturedMesh(v_pos=torch.zeros((3, 3), device=wr_ctx.device),
+                           t_pos_idx=torch.zeros((0, 3), dtype=torch.int64, device=wr_ctx.device))
+    mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    out = wr.render(wr_ctx, mesh, cam, 32, 48, render_attr=False, normal_background=0.5)
+    assert not bool(out.mask.any()) and float(out.pos.abs().max()) == 0.0
+    assert float((out.normal - 0.5).abs().max()) == 0.0 and float(out.depth.abs().max()) == 0.0

@@ -102,7 +102,7 @@ def test_perspective_correct_barycentrics():
     np.testing.assert_allclose(clip[:2] / clip[3], [px, py], atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["soup", "ties", "fan", "near", "mix"])
+@pytest.mark.parametrize("name", ["soup", "ties", "fan", "near", "mix", "guard"])
 def test_c_oracle_equals_numpy_twin(name):
     pos, tri, res = {
         "soup": (*cases.random_soup(3, 60, B=2, perspective=True), (40, 56)),
@@ -110,6 +110,7 @@ def test_c_oracle_equals_numpy_twin(name):
         "fan": (*cases.shared_edge_fan(12), (33, 33)),
         "near": (*cases.near_crossing_scene(5, 40), (32, 48)),
         "mix": (*cases.big_and_small_mix(9), (48, 48)),
+        "guard": (*cases.guard_band_scene(13, 24), (40, 40)),
     }[name]
     if name == "mix":
         pos, tri = pos[:, :309], tri[:103]  # keep the pure-Python twin fast
