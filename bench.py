@@ -314,8 +314,16 @@ def run_ours(args):
             slot["w2c"].copy_(w2c_host, non_blocking=True)
             slot["ready"].record(s_h2d)
 
+    pending = [None, None]  # render outputs of the step that last used each host buffer set
+
     def render_and_read_back(k):
         slot = dev_in[k % 2]
+        # The maps of step k-2 are released here.  Their copy must be complete before the main stream may reuse
+        # that memory, so the wait is put on the main stream BEFORE the references are dropped (no
+        # record_stream: the caching allocator then recycles the blocks at once and never has to grow).
+        if pending[k % 2] is not None:
+            main.wait_event(d2h_done[k % 2])
+            pending[k % 2] = None
         main.wait_event(slot["ready"])
         m = make_mesh(slot["v"], slot["f"])
         c = wr.Camera(c2w=None, w2c=slot["w2c"], proj_mtx=cam.proj_mtx, mvp_mtx=slot["mvp"], cam_pos=None)
@@ -325,12 +333,10 @@ def run_ours(args):
         done.record(main)
         with torch.cuda.stream(s_d2h):
             s_d2h.wait_event(done)
-            s_d2h.wait_event(d2h_done[k % 2])  # the host buffer of two steps ago has been consumed
             for name, dst in host_outs[k % 2].items():
-                src = getattr(o, name)
-                src.record_stream(s_d2h)
-                dst.copy_(src, non_blocking=True)
+                dst.copy_(getattr(o, name), non_blocking=True)
             d2h_done[k % 2].record(s_d2h)
+        pending[k % 2] = (o, m)
 
     def e2e_run(n):
         for slot in dev_in:
@@ -341,8 +347,9 @@ def run_ours(args):
                 upload(k + 1)
             render_and_read_back(k)
         torch.cuda.synchronize()
+        pending[0] = pending[1] = None
 
-    e2e_run(3)
+    e2e_run(6)
     barrier()
     Ke = min(K, 30)
     t0 = time.perf_counter()
