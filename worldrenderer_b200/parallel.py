@@ -166,6 +166,24 @@ def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group) -> Optiona
     return ws
 
 
+_PRE_CACHE: Dict[int, tuple] = {}
+
+
+def _uv_precompute_cached(ctx, mesh, uv_size: int):
+    """uv_precompute is replicated on every rank and depends on the mesh and atlas size only: keep the last one
+    per device while the mesh tensors are unchanged (same storage and version), like CameraProjection does."""
+    from .uv import UVPrecomputeOutput, uv_precompute
+    srcs = (mesh.v_pos, mesh.t_pos_idx, mesh.v_tex, mesh.t_tex_idx)
+    key = (int(uv_size),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+    slot = ctx.device.index
+    hit = _PRE_CACHE.get(slot)
+    if hit is None or hit[0] != key:
+        pre = uv_precompute(ctx, mesh, uv_size, uv_size)
+        hit = (key, srcs, pre.uv_mask, pre.uv_pos)
+        _PRE_CACHE[slot] = hit
+    return UVPrecomputeOutput(height=uv_size, width=uv_size, uv_attr=mesh.texture, uv_mask=hit[2], uv_pos=hit[3])
+
+
 def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_size: int, *, view_masks_local=None,
                  aoi_cos_valid_threshold: float = 0.3, depth_grad_dilation: int = 5,
                  depth_grad_threshold: Optional[float] = 0.1, uv_exp_blend_alpha: float = 6.0,
@@ -177,10 +195,10 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
               "nccl" -- all_reduce(SUM) of the accumulators, then wr_uv_finalize on every rank;
               "auto" -- p2p when symmetric memory is available for the group, else nccl.
     With "p2p" / "auto" the returned tensors are views of the workspace: valid until the next bake of that size."""
-    from .uv import fused_unproject, fused_view_maps, uv_finalize, uv_precompute
+    from .uv import fused_unproject, fused_view_maps, uv_finalize
     if exchange not in ("auto", "p2p", "nccl"):
         raise ValueError(f"exchange={exchange!r}")
-    pre = uv_precompute(ctx, mesh, uv_size, uv_size)
+    pre = _uv_precompute_cached(ctx, mesh, uv_size)
     ws = _p2p_workspace(uv_size, uv_size, ctx.device, group) if exchange != "nccl" else None
     if exchange == "p2p" and ws is None:
         raise RuntimeError("exchange='p2p' requested but peer memory is not available for this process group")
