@@ -13,9 +13,14 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-NV, RES, UV = 32, 1024, 2048
-v, f = bench.terrain_arrays(0)
-vt = synth.terrain_uv(bench.TERRAIN[0], bench.TERRAIN[1]).astype(np.float32)
+FULL = os.environ.get("WR_CONFIG_E", "0") == "1"  # the full config E: 5M faces, 32 x 2048^2 views, 4096^2 atlas
+NV, RES, UV = (32, 2048, 4096) if FULL else (32, 1024, 2048)
+NX, NY = (2500, 1000) if FULL else bench.TERRAIN
+v, f = synth.terrain(NX, NY, 0)
+v = v / np.abs(v).max() * 0.5
+v = np.ascontiguousarray(np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1), np.float32)
+f = np.ascontiguousarray(f, np.int64)
+vt = synth.terrain_uv(NX, NY).astype(np.float32)
 mesh = wr.TexturedMesh(v_pos=torch.from_numpy(v), t_pos_idx=torch.from_numpy(f), v_tex=torch.from_numpy(vt),
                        t_tex_idx=torch.from_numpy(f).clone(), texture=torch.zeros((UV, UV, 3)))
 mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
