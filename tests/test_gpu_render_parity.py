@@ -84,6 +84,10 @@ def test_tri_ids_and_rast_fused(wr_ctx):
         np.testing.assert_allclose(raw["pos"].cpu().numpy(), ref["pos"], rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(raw["normal"].cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(raw["depth"].cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
+        # Stronger than the 1e-5 bar: the kernels issue the same individually rounded operations in the same order
+        # as the oracle (-fmad=false, IEEE div / sqrt), so every float map is identical bit for bit.
+        for k in ("rast", "pos", "normal", "depth"):
+            np.testing.assert_array_equal(raw[k].cpu().numpy(), ref[k], err_msg=k)
 
 
 def test_custom_strategy_and_backgrounds(wr_ctx):
@@ -224,6 +228,8 @@ def test_config_b_full_size_bit_exact_ids_against_oracle(wr_ctx):
     np.testing.assert_allclose(raw["pos"].cpu().numpy(), ref["pos"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(raw["normal"].cpu().numpy(), ref["normal"], rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(raw["depth"].cpu().numpy(), ref["depth"], rtol=RTOL, atol=ATOL)
+    for k in ("pos", "normal", "depth"):  # bit-identical as well (see test_tri_ids_and_rast_fused)
+        np.testing.assert_array_equal(raw[k].cpu().numpy(), ref[k], err_msg=k)
     assert ref["mask"].sum() > 700_000
 
 
