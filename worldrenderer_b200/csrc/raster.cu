@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
 }
 
 // One warp rasterises one snapped triangle (or the stripe-th share of its 16x16 blocks).
-// E is the integer type of the edge functions: int when the snapped extent is below 2^15 (products < 2^30),
+// E is the integer type of the edge functions: int when the snapped extent is below 2^14 (products < 2^29),
 // long long otherwise (coordinates up to 2^22).  Both are exact, so the choice cannot change a result.
 template <typename E> __device__ __forceinline__ float edge_to_float(E e);
 template <> __device__ __forceinline__ float edge_to_float<int>(int e) { return __int2float_rn(e); }
@@ -286,27 +286,38 @@ __device__ void warp_raster_impl(int x0, int y0, int x1, int y1, int x2, int y2,
     const float inv_area = 1.0f / __ll2float_rn(area2);
     const int lx = lane & 7, ly = lane >> 3;
 
-    auto footprint = [&](int fx, int fy, int cl, int ch, int rl, int rh) {
-        const int cc = fx + lx, rr = fy + ly;
-        const int px = 16 * cc + ox, py = 16 * rr + oy;
-        const E e0 = (E)dx0 * (py - y1) - (E)dy0 * (px - x1);
-        const E e1 = (E)dx1 * (py - y2) - (E)dy1 * (px - x2);
-        const E e2 = (E)dx2 * (py - y0) - (E)dy2 * (px - x0);
-        const bool cov = cc >= cl && cc <= ch && rr >= rl && rr <= rh && e0 >= bias0 && e1 >= bias1 && e2 >= bias2;
-        if (__ballot_sync(0xFFFFFFFFu, cov) == 0) return;
-        if (cov) {
-            const float b0 = edge_to_float<E>(e0) * inv_area;
-            const float b1 = edge_to_float<E>(e1) * inv_area;
-            const float b2 = (1.0f - b0) - b1;
-            float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
-            zw = zw + 0.0f;
-            if (zw >= -1.0f && zw <= 1.0f) resolve_sample(depth_view + (size_t)rr * W + cc, zw, id);
+    // Walks the 8x4-pixel footprints of the pixel rectangle [cl,ch] x [rl,rh].  The three edge functions are
+    // evaluated once per footprint row for this lane's pixel and then advanced by a constant per 8-pixel step
+    // (exact integer arithmetic either way).
+    const E sx0 = -(E)dy0 * 128, sx1 = -(E)dy1 * 128, sx2 = -(E)dy2 * 128;  // +8 pixels in x = +128 sub-pixel units
+    auto scan = [&](int cl, int ch, int rl, int rh) {
+        for (int fy = rl & ~3; fy <= rh; fy += 4) {
+            const int rr = fy + ly;
+            const bool row_in = rr >= rl && rr <= rh;
+            const int py = 16 * rr + oy;
+            int cc = (cl & ~7) + lx;
+            const int px = 16 * cc + ox;
+            E e0 = (E)dx0 * (py - y1) - (E)dy0 * (px - x1);
+            E e1 = (E)dx1 * (py - y2) - (E)dy1 * (px - x2);
+            E e2 = (E)dx2 * (py - y0) - (E)dy2 * (px - x0);
+            unsigned long long *row = depth_view + (size_t)rr * W;
+            for (int fx = cl & ~7; fx <= ch; fx += 8, cc += 8, e0 += sx0, e1 += sx1, e2 += sx2) {
+                const bool cov = row_in && cc >= cl && cc <= ch && e0 >= bias0 && e1 >= bias1 && e2 >= bias2;
+                if (__ballot_sync(0xFFFFFFFFu, cov) == 0) continue;
+                if (cov) {
+                    const float b0 = edge_to_float<E>(e0) * inv_area;
+                    const float b1 = edge_to_float<E>(e1) * inv_area;
+                    const float b2 = (1.0f - b0) - b1;
+                    float zw = ((z0 * b0) + (z1 * b1)) + (z2 * b2);
+                    zw = zw + 0.0f;
+                    if (zw >= -1.0f && zw <= 1.0f) resolve_sample(row + cc, zw, id);
+                }
+            }
         }
     };
 
     if (!LARGE) {
-        for (int fy = r0 & ~3; fy <= r1; fy += 4)
-            for (int fx = c0 & ~7; fx <= c1; fx += 8) footprint(fx, fy, c0, c1, r0, r1);
+        scan(c0, c1, r0, r1);
     } else {
         constexpr int kB = 1 << kLargeBlockLog2;
         const int bx0 = c0 >> kLargeBlockLog2, bx1 = c1 >> kLargeBlockLog2, by0 = r0 >> kLargeBlockLog2,
@@ -323,8 +334,7 @@ __device__ void warp_raster_impl(int x0, int y0, int x1, int y1, int x2, int y2,
             const E m1 = (E)dx1 * ((dx1 >= 0 ? pyh : pyl) - y2) - (E)dy1 * ((dy1 >= 0 ? pxl : pxh) - x2);
             const E m2 = (E)dx2 * ((dx2 >= 0 ? pyh : pyl) - y0) - (E)dy2 * ((dy2 >= 0 ? pxl : pxh) - x0);
             if (m0 < bias0 || m1 < bias1 || m2 < bias2) continue;
-            for (int fy = rl & ~3; fy <= rh; fy += 4)
-                for (int fx = cl & ~7; fx <= ch; fx += 8) footprint(fx, fy, cl, ch, rl, rh);
+            scan(cl, ch, rl, rh);
         }
     }
 }
@@ -336,7 +346,8 @@ __device__ __forceinline__ void warp_raster(int x0, int y0, int x1, int y1, int 
 {
     const int ext_x = max(x0, max(x1, x2)) - min(x0, min(x1, x2));
     const int ext_y = max(y0, max(y1, y2)) - min(y0, min(y1, y2));
-    if (ext_x < 32768 && ext_y < 32768)
+    // int32 is exact while every product stays below 2^29: extent < 2^14 (1024 px) plus the 8x4 footprint overhang
+    if (ext_x < 16384 && ext_y < 16384)
         warp_raster_impl<LARGE, int>(x0, y0, x1, y1, x2, y2, z0, z1, z2, id, W, H, depth_view, stripe, lane);
     else
         warp_raster_impl<LARGE, long long>(x0, y0, x1, y1, x2, y2, z0, z1, z2, id, W, H, depth_view, stripe, lane);
