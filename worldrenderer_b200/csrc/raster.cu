@@ -40,8 +40,13 @@ __device__ __forceinline__ int floor_div16(int a) { return a >> 4; }
 __device__ __forceinline__ int ceil_div16(int a) { return -((-a) >> 4); }
 __device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
 
-__global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, int W, int H, SnapVert *sv)
+// Both snap kernels also clear the per-view counter / depth-range block (consumed by the kernels launched after
+// them on the same stream), which saves a separate memset launch.
+__global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, int W, int H, SnapVert *sv, int *stats,
+                                                       int nstats)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0)
+        for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + view0;
     if (v >= src.V) return;
@@ -210,8 +215,11 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
 }
 
 // All views of a vertex in one thread: the position is read once, B independent snap chains.
-__global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int B, int W, int H, SnapVert *sv)
+__global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int B, int W, int H, SnapVert *sv,
+                                                                int *stats, int nstats)
 {
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= src.V) return;
     const float *p = src.pos + 3 * (size_t)v;
@@ -236,9 +244,12 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
         oc |= (c.z > c.w) ? 32u : 0u;
         flags |= oc << WR_SV_OC_SHIFT;
         if (c.w > 0.0f) {
-            const float rw = 1.0f / c.w;
-            const float fx = (c.x * (float)(8 * W)) * rw;
-            const float fy = (c.y * (float)(8 * H)) * rw;
+            // w == 1 exactly (orthographic rows 0 0 0 1): rw == 1 and (a * 1) == a, so the divide and the three
+            // multiplications can be skipped without changing a bit
+            const bool unit_w = c.w == 1.0f;
+            const float rw = unit_w ? 1.0f : 1.0f / c.w;
+            const float fx = unit_w ? (c.x * (float)(8 * W)) : (c.x * (float)(8 * W)) * rw;
+            const float fy = unit_w ? (c.y * (float)(8 * H)) : (c.y * (float)(8 * H)) * rw;
             if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
                 s.x = __float2int_rn(fx);
                 s.y = __float2int_rn(fy);
@@ -544,22 +555,25 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset depth");
     }
     ctx->clean_bytes = 0;  // dirty until the consuming kernel has been launched
-    e = cudaMemsetAsync(stats, 0, (size_t)B * 8 * sizeof(int), stream);
-    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset counters");
+    const bool have_work = F > 0 && V > 0 && B > 0;
+    if (!have_work) {  // no snap kernel will run: clear the counter block here
+        e = cudaMemsetAsync(stats, 0, (size_t)B * 8 * sizeof(int), stream);
+        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset counters");
+    }
     res->packed = depth;
     res->packed_bytes = packed_bytes;
     res->view_stats = stats + 4 * B;
 
-    if (F > 0 && V > 0 && B > 0) {
+    if (have_work) {
         RasterParams P;
         P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
         const int qgrid = ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
         if (src.mvp)
-            k_snap_vertices_allviews<<<wr_div_up(V, 256), 256, 0, stream>>>(src, B, W, H, sv);
+            k_snap_vertices_allviews<<<wr_div_up(V, 256), 256, 0, stream>>>(src, B, W, H, sv, stats, B * 8);
         else
-            k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv);
+            k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv, stats, B * 8);
         WR_CHECK_LAUNCH(ctx, "k_snap_vertices");
         if (!tri_ranges) {
             wr_stage(ctx, stream, "k_setup_triangles");
