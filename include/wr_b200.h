@@ -112,7 +112,7 @@ typedef struct wr_render_args {
     int TH, TW, TC;
     int tex_filter;           /* 0 nearest, 1 linear */
     /* cameras */
-    const float *mvp;         /* [B,4,4] row major */
+    const float *mvp;         /* [B,4,4] row major, 16-byte aligned */
     const float *w2c;         /* [B,4,4] */
     int B, H, W;
     /* depth */

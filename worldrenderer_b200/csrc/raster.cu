@@ -220,17 +220,30 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
 {
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
+    // the B view matrices are staged in shared memory once per block (16-byte broadcast reads instead of 16
+    // global loads per view and thread); views beyond the staging capacity read global memory
+    constexpr int kStageViews = 32;
+    __shared__ float4 s_mvp[kStageViews * 4];
+    for (int i = threadIdx.x; i < min(B, kStageViews) * 4; i += blockDim.x)
+        s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
+    __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= src.V) return;
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
     for (int b = 0; b < B; ++b) {
-        const float *m = src.mvp + 16 * b;
+        float4 r0, r1, r2, r3;
+        if (b < kStageViews) {
+            r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
+        } else {
+            const float4 *m4 = reinterpret_cast<const float4 *>(src.mvp) + 4 * b;
+            r0 = __ldg(m4); r1 = __ldg(m4 + 1); r2 = __ldg(m4 + 2); r3 = __ldg(m4 + 3);
+        }
         float4 c;
-        c.x = ((m[0] * x + m[1] * y) + m[2] * z) + m[3];
-        c.y = ((m[4] * x + m[5] * y) + m[6] * z) + m[7];
-        c.z = ((m[8] * x + m[9] * y) + m[10] * z) + m[11];
-        c.w = ((m[12] * x + m[13] * y) + m[14] * z) + m[15];
+        c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
+        c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
+        c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
+        c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
         SnapVert s;
         s.x = 0; s.y = 0; s.zw = 0.0f;
         uint32_t flags = 0;

@@ -381,6 +381,7 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     if (A.F >= (1 << 30)) return WR_ERR_UNSUPPORTED;
     if (A.B == 0) return WR_OK;
     if (!A.mvp || (A.V > 0 && !A.v_pos) || (A.F > 0 && !A.tri)) return WR_ERR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(A.mvp) & 15u) return WR_ERR_INVALID_ARGUMENT;  // read as float4 rows
     if (A.out_depth && !A.w2c) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_normal && !A.v_nrm) return WR_ERR_INVALID_ARGUMENT;
     if (A.out_geo && (!A.v_nrm || !A.w2c)) return WR_ERR_INVALID_ARGUMENT;
