@@ -474,10 +474,19 @@ def bench_bake(ctx, dev, flush_buf):
         unproj_ms = timed(lambda: fused_unproject(ctx, pre, cam, H, W, geo, att, aoi_cos_thresh=0.2,
                                                   depth_grad_thresh=0.1, alpha=3.0,
                                                   view_weight=torch.ones(N_VIEWS, device=dev)))
+        # the reference's default tail (uv.py:426-461): seam padding, and Poisson blending with 1000 sweeps
+        proj_pb = wr.CameraProjection("torch-cuda", None, str(dev), "cuda")
+        proj_pb.ctx = ctx
+        kw_pad = dict(kw, uv_padding=True)
+        kw_pb = dict(kw, uv_padding=True, poisson_blending=True, pb_num_iters=1000)
+        pad_ms = timed(lambda: proj_pb(images, mesh, cam, **kw_pad), reps=10)
+        pb_ms = timed(lambda: proj_pb(images, mesh, cam, **kw_pb), reps=5)
     peak, _ = peaks()
     bytes_unproj = 32 * N_VIEWS * H * W + 38 * uv * uv
     return {"workload": "config C: 50k-face icosphere, 6 x 768^2 images -> 1024^2 atlas, validity + cosine^3 weights",
             "ms_per_uv_bake_end_to_end": e2e_ms, "ms_unprojection_only": unproj_ms,
+            "ms_per_uv_bake_with_seam_padding": pad_ms,
+            "ms_per_uv_bake_with_padding_and_poisson_1000_sweeps": pb_ms,
             "unprojection_algorithmic_bytes": bytes_unproj,
             "unprojection_frac_of_hbm_peak": bytes_unproj / (unproj_ms * 1e-3) / 1e9 / peak}
 

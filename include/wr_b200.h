@@ -29,6 +29,8 @@
  *   wr_grid_sample                   F.grid_sample as used by uv_render_attr uv.py:200-218 (operator form)
  *   wr_uv_finalize                   hard stitch with the existing texture uv.py:452-455 (after the
  *                                    optional multi-GPU all-reduce of the accumulators)
+ *   wr_poisson_blend                 PoissonBlendingSolver.__call__ blend.py:214-324 (Jacobi kernel blend.py:60-100)
+ *   wr_uv_padding / wr_inpaint_u8    uv_padding uv.py:373-382 -> inpaint_cvc cv_ops.py:11-35 (cvcuda.inpaint)
  *
  * The raster contract (snap, fill rule, depth key, tie break) is DESIGN.md section 3.
  */
@@ -221,6 +223,32 @@ int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *args, void 
  */
 int wr_grid_sample(wr_ctx *ctx, const float *map, int B, int H, int W, int C, const float *ndc, int Hs, int Ws,
                    float *out, void *stream);
+
+/*
+ * PoissonBlendingSolver.__call__ (blend.py:214-324).  src (guidance), tgt: [H,W,C] f32, C <= 4; mask: [H,W] u8,
+ * non-zero = solve region (the caller applies the > 0.5 threshold of blend.py:229-232; the image border is
+ * removed here, blend.py:233-236).  grad_mode: 0 "src", 1 "max", 2 "avg" (blend.py:243-281).  Exactly
+ * num_iters Jacobi sweeps x <- (sum of the 4 neighbours + b) / 4 (blend.py:69).  out: [H,W,C] = tgt outside
+ * the region, clamp(x, 0, 1) inside (blend.py:317-321); out may alias tgt only if tgt is not needed afterwards
+ * (inplace=True) -- it is read by the first and written by the last kernel only.
+ */
+int wr_poisson_blend(wr_ctx *ctx, const float *src, const uint8_t *mask, const float *tgt, int H, int W, int C,
+                     int num_iters, int grad_mode, float *out, void *stream);
+
+/*
+ * Seam fill standing in for cvcuda.inpaint(image, mask, radius) (cv_ops.py:32; third-party operator, absent):
+ * pixels with mask != 0 are replaced by an inverse-square-distance average of the known pixels within `radius`
+ * of their nearest known pixel; known pixels are copied.  img, out: [H,W,C] u8, C <= 4.
+ */
+int wr_inpaint_u8(wr_ctx *ctx, const uint8_t *img, const uint8_t *mask, int H, int W, int C, int radius,
+                  uint8_t *out, void *stream);
+/*
+ * uv_padding (uv.py:373-382) in one call: attr [H,W,C] f32 is clamped to [0,1] and quantised as (x * 255)
+ * truncated to u8 (cv_ops.py:23-24), texels with inside_mask == 0 are filled as in wr_inpaint_u8, and the result is
+ * returned as u8 / 255 (cv_ops.py:35) -- known texels come back quantised, like in the reference.
+ */
+int wr_uv_padding(wr_ctx *ctx, const float *attr, const uint8_t *inside_mask, int H, int W, int C, int radius,
+                  float *out, void *stream);
 
 #ifdef __cplusplus
 }

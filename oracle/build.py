@@ -1,6 +1,6 @@
 """Build recipe for the CPU oracle (test infrastructure, not product code).
 
-Compiles oracle/wr_oracle.c -> oracle/_build/libwr_oracle.so with gcc.  `-ffp-contract=off`
+Compiles oracle/wr_oracle.c + oracle/wr_oracle_blend.c -> oracle/_build/libwr_oracle.so with gcc.  `-ffp-contract=off`
 is REQUIRED: the raster contract is a sequence of individually rounded
 fp32 operations and a fused multiply-add would change coverage at snap boundaries.
 
@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "wr_oracle.c")
+SRCS = [os.path.join(HERE, "wr_oracle.c"), os.path.join(HERE, "wr_oracle_blend.c")]
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libwr_oracle.so")
 
@@ -25,9 +25,9 @@ CFLAGS = ["-O2", "-fPIC", "-shared", "-std=c11", "-fopenmp", "-ffp-contract=off"
 
 def build(force: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in SRCS):
         return LIB
-    cmd = ["gcc", *CFLAGS, SRC, "-o", LIB, "-lm"]
+    cmd = ["gcc", *CFLAGS, *SRCS, "-o", LIB, "-lm"]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -175,6 +175,52 @@ def bake_cases(mu):
     np.savez_compressed(os.path.join(OUT, "bake_sphere.npz"), **out)
 
 
+def poisson_cases(mu):
+    """The reference's own PoissonBlendingSolver (blend.py:186-324) on CPU, "torch-native" backend, unmodified;
+    then its uv_blend / CameraProjection with Poisson blending + padding, where only cvcuda.inpaint is served by the
+    oracle's fill (ref_shim._make_cvcuda) -- that pins the control flow of uv.py:426-461, not the fill."""
+    import importlib
+    blend = importlib.import_module("mvadapter.utils.mesh_utils.blend")
+    solver = blend.PoissonBlendingSolver("torch-native", "cpu")
+    rng = np.random.default_rng(7)
+    H, W = 56, 72
+    yy, xx = np.mgrid[0:H, 0:W]
+    src = (0.5 + 0.4 * np.sin(0.3 * xx + 0.2 * yy)[..., None] * np.array([1, 0.8, 0.6]) + 0.05 * rng.random((H, W, 3)))
+    tgt = (0.4 + 0.3 * np.cos(0.15 * xx - 0.25 * yy)[..., None] * np.array([0.7, 1, 0.5]) + 0.05 * rng.random((H, W, 3)))
+    src, tgt = src.astype(np.float32), tgt.astype(np.float32)
+    mask = np.zeros((H, W), np.float32)
+    mask[5:30, 3:60] = 1
+    mask[10:12, 10:20] = 0
+    mask[0:3, :] = 1          # touches the border: removed by blend.py:233-236
+    mask[40:56, 60:72] = 1
+    mask[35, 5] = 1           # isolated pixel
+    out = {"src": src, "tgt": tgt, "mask": mask}
+    for gm in ("src", "max", "avg"):
+        for it in (0, 1, 9, 250):
+            r = solver(torch.from_numpy(src), torch.from_numpy(mask), torch.from_numpy(tgt).clone(), it,
+                       inplace=False, grad_mode=gm)
+            out[f"{gm}_{it}"] = _np(r)
+    r = solver(torch.from_numpy(src), torch.from_numpy(np.repeat(mask[..., None], 3, -1)), torch.from_numpy(tgt).clone(),
+               16, inplace=False)
+    out["mask3_16"] = _np(r)
+
+    # bake with the post-processing tail
+    m = _sphere_mesh(mu, 6, 64, seed=2)
+    cam = mu.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    images = synth.view_images(6, 48, 48, seed=1)
+    proj = mu.CameraProjection(pb_backend="torch-native", bg_remover=None, device="cpu", context_type="cuda")
+    kw = dict(uv_size=64, iou_rejection_threshold=None, aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
+              uv_exp_blend_alpha=3.0, depth_grad_dilation=5)
+    out["bake_pad"] = _np(proj(torch.from_numpy(images), m, cam, poisson_blending=False, uv_padding=True, **kw))
+    out["bake_pad_scratch"] = _np(proj(torch.from_numpy(images), m, cam, poisson_blending=False, uv_padding=True,
+                                       from_scratch=True, **kw))
+    out["bake_pb"] = _np(proj(torch.from_numpy(images), m, cam, poisson_blending=True, pb_num_iters=40,
+                              uv_padding=True, **kw))
+    out["bake_pb_noborder"] = _np(proj(torch.from_numpy(images), m, cam, poisson_blending=True, pb_num_iters=40,
+                                       pb_keep_original_border=False, uv_padding=True, **kw))
+    np.savez_compressed(os.path.join(OUT, "poisson.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -185,6 +231,7 @@ def main():
     load_mesh_cases(mu)
     render_cases(mu)
     bake_cases(mu)
+    poisson_cases(mu)
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
 

@@ -8,7 +8,8 @@ the NumPy restatement in oracle/render_oracle.py is pinned against the reference
 The reference imports several third-party modules that are absent from this image
 (nvdiffrast, trimesh, cvcuda, imageio, matplotlib, omegaconf, ...).  None of them is touched
 on the hot path, so they are replaced by empty stub modules; `nvdiffrast.torch` gets a real
-CPU implementation of the four names the path calls.
+CPU implementation of the four names the path calls, and `cvcuda` the two names cv_ops.py's
+inpaint_cvc calls (served by the oracle's own seam fill, see _make_cvcuda).
 """
 from __future__ import annotations
 
@@ -71,7 +72,32 @@ def _make_dr() -> types.ModuleType:
     return dr
 
 
-_STUBS = ["trimesh", "cvcuda", "imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
+def _make_cvcuda() -> types.ModuleType:
+    """`cvcuda` as far as the reference's cv_ops.py:1-35 touches it.  `inpaint` is served by the oracle's
+    statement of the seam fill (wr_oracle_blend.c) -- NOT by CV-CUDA's algorithm, which is absent here; it lets
+    the reference's own uv_padding / uv_blend control flow (uv.py:373-382, 426-461) run unmodified on CPU."""
+    cv = types.ModuleType("cvcuda")
+
+    class _T:
+        def __init__(self, t):
+            self.t = t
+
+        def cuda(self):
+            return self.t
+
+    def as_tensor(x, layout=None):
+        return _T(x)
+
+    def inpaint(image, mask, radius):
+        out = shim.inpaint_u8(image.t.detach().cpu().numpy(), mask.t.detach().cpu().numpy(), int(radius))
+        return _T(torch.from_numpy(out))
+
+    cv.as_tensor = as_tensor
+    cv.inpaint = inpaint
+    return cv
+
+
+_STUBS = ["trimesh", "imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
           "matplotlib.colors", "omegaconf", "pytorch_lightning", "jaxtyping", "typeguard",
           "spandrel", "gltflib", "pymeshlab", "open3d"]
 
@@ -87,6 +113,8 @@ def load_reference():
         pkg.torch = dr
         sys.modules["nvdiffrast"] = pkg
         sys.modules["nvdiffrast.torch"] = dr
+    if "cvcuda" not in sys.modules or not hasattr(sys.modules["cvcuda"], "inpaint"):
+        sys.modules["cvcuda"] = _make_cvcuda()
     for name in _STUBS:
         try:
             importlib.import_module(name)

@@ -313,19 +313,44 @@ def uv_blend(pre: dict, geo: dict, attr: Optional[dict], uv_attr_old=None, **kw)
     blend = (attr["uv_attr_proj"] * weight[..., None]).sum(0, dtype=f32)                      # uv.py:421-423
     old = np.zeros_like(blend) if uv_attr_old is None else _a(uv_attr_old)
     va = valid_any[..., None].astype(f32)
-    out["uv_attr_blend"] = (blend * va + old * (f32(1) - va)).astype(f32)                      # uv.py:452-455
+    stitched = (blend * va + old * (f32(1) - va)).astype(f32)                                  # uv.py:452-455
+    pkw = {k: kw[k] for k in ("do_uv_padding", "uv_padding_radius", "pad_unseen_area", "poisson_blending",
+                              "pb_num_iters", "pb_keep_original_border", "pb_grad_mode") if k in kw}
+    out["uv_attr_blend"] = atlas_postprocess(blend, stitched, valid_any, pre["uv_mask"], old, **pkw)
     return out
 
 
+def atlas_postprocess(blend, stitched, valid_any, uv_mask, old, do_uv_padding=False, uv_padding_radius=3,
+                      pad_unseen_area=False, poisson_blending=False, pb_num_iters=1000,
+                      pb_keep_original_border=True, pb_grad_mode="src", nthreads: int = 0):
+    """uv.py:426-461: optional Poisson blend (blend.py, exact sweep count) and seam padding (the oracle's
+    statement of the fill that stands in for cvcuda.inpaint, wr_oracle_blend.c)."""
+    if poisson_blending:
+        assert do_uv_padding                                                                   # uv.py:427
+        padded = shim.uv_padding(blend, valid_any, uv_padding_radius, nthreads)                # uv.py:429-431
+        if pb_keep_original_border:
+            tgt = old                                                                          # uv.py:432-433
+        else:
+            tgt = shim.uv_padding(stitched, uv_mask, uv_padding_radius, nthreads)              # uv.py:435-443
+        res = shim.poisson_blend(padded, valid_any, tgt, pb_num_iters, pb_grad_mode, nthreads)  # uv.py:445-452
+    else:
+        res = stitched
+    if do_uv_padding:                                                                          # uv.py:457-461
+        res = shim.uv_padding(res, valid_any if pad_unseen_area else uv_mask, uv_padding_radius, nthreads)
+    return res
+
+
 # ---------------------------------------------------------------------------------------------
-# projection.py:54-204  CameraProjection.__call__ (poisson_blending=False, uv_padding=False,
-# warp_images=False; the IoU rejection of :125-138 is evaluated and reported)
+# projection.py:54-204  CameraProjection.__call__ (warp_images=False; the IoU rejection of :125-138 is
+# evaluated and reported)
 # ---------------------------------------------------------------------------------------------
 
 def camera_projection(images, v_pos, tri, v_nrm, tri_nrm, v_tex, tri_tex, texture, mvp, w2c, uv_size: int,
                       masks=None, iou_rejection_threshold=0.8, aoi_cos_valid_threshold=0.3,
                       depth_grad_dilation=5, depth_grad_threshold=0.1, uv_exp_blend_alpha=6.0,
-                      uv_exp_blend_view_weight=None, nthreads: int = 0) -> Optional[dict]:
+                      uv_exp_blend_view_weight=None, poisson_blending=False, pb_num_iters=1000,
+                      pb_keep_original_border=True, from_scratch=False, uv_padding=False,
+                      nthreads: int = 0) -> Optional[dict]:
     images = _a(images)
     Nv, H, W, _ = images.shape
     m = None
@@ -347,7 +372,9 @@ def camera_projection(images, v_pos, tri, v_nrm, tri_nrm, v_tex, tri_tex, textur
     attr = uv_render_attr(images, geo, m)                                                     # projection.py:165-169
     bl = uv_blend(pre, geo, attr, uv_attr_old=texture, aoi_cos_thresh=aoi_cos_valid_threshold,
                   depth_grad_thresh=depth_grad_threshold, alpha=uv_exp_blend_alpha,
-                  view_weight=uv_exp_blend_view_weight)                                       # projection.py:170-188
+                  view_weight=uv_exp_blend_view_weight, do_uv_padding=uv_padding, pad_unseen_area=from_scratch,
+                  poisson_blending=poisson_blending, pb_num_iters=pb_num_iters,
+                  pb_keep_original_border=pb_keep_original_border)                            # projection.py:170-188
     return {"uv_proj": bl["uv_attr_blend"], "uv_proj_mask": bl["uv_valid_mask_blend"],
             "uv_depth_grad": geo["uv_depth_grad"], "uv_aoi_cos": geo["uv_aoi_cos"],
             "pre": pre, "geo": geo, "attr": attr, "blend": bl}

@@ -18,6 +18,7 @@ _LIB: Optional[ctypes.CDLL] = None
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 _i32p = ctypes.POINTER(ctypes.c_int32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
 
 
 def lib() -> ctypes.CDLL:
@@ -38,6 +39,12 @@ def lib() -> ctypes.CDLL:
         L.wro_clip_positions.restype = ctypes.c_int
         L.wro_clip_positions.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int]
         L.wro_num_threads.restype = ctypes.c_int
+        L.wro_poisson_blend.restype = ctypes.c_int
+        L.wro_poisson_blend.argtypes = [_f32p, _u8p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, _f32p, ctypes.c_int]
+        L.wro_inpaint.restype = ctypes.c_int
+        L.wro_inpaint.argtypes = [_u8p, _u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u8p,
+                                  ctypes.c_int]
         _LIB = L
     return _LIB
 
@@ -123,3 +130,44 @@ def clip_positions(v_pos, mvp, nthreads: int = 0):
     if rc != 0:
         raise RuntimeError(f"wro_clip_positions failed with status {rc}")
     return out
+
+
+_GRAD_MODE = {"src": 0, "max": 1, "avg": 2}
+
+
+def poisson_blend(src, mask, tgt, num_iters: int, grad_mode: str = "src", nthreads: int = 0):
+    """PoissonBlendingSolver.__call__ (blend.py:214-324) with exactly `num_iters` Jacobi sweeps.
+    src, tgt [H,W,C] f32; mask [H,W] bool (already thresholded) -> [H,W,C] f32."""
+    src = _f32(src)
+    tgt = _f32(tgt)
+    m = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+    H, W, C = tgt.shape
+    assert src.shape == tgt.shape and m.shape == (H, W)
+    out = np.empty_like(tgt)
+    rc = lib().wro_poisson_blend(_fp(src), m.ctypes.data_as(_u8p), _fp(tgt), H, W, C, int(num_iters),
+                                 _GRAD_MODE[grad_mode], _fp(out), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"wro_poisson_blend failed with status {rc}")
+    return out
+
+
+def inpaint_u8(img, mask, radius: int, nthreads: int = 0):
+    """The seam fill that stands in for cvcuda.inpaint (cv_ops.py:32): img [H,W,C] u8, mask [H,W] (non-zero = fill)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    m = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+    H, W, C = img.shape
+    assert m.shape == (H, W)
+    out = np.empty_like(img)
+    rc = lib().wro_inpaint(img.ctypes.data_as(_u8p), m.ctypes.data_as(_u8p), H, W, C, int(radius),
+                           out.ctypes.data_as(_u8p), nthreads)
+    if rc != 0:
+        raise RuntimeError(f"wro_inpaint failed with status {rc}")
+    return out
+
+
+def uv_padding(attr, inside_mask, radius: int, nthreads: int = 0):
+    """uv_padding (uv.py:373-382) over inpaint_cvc's quantisation (cv_ops.py:23-35): float in, float out."""
+    a = np.clip(_f32(attr), 0.0, 1.0)
+    q = (a * np.float32(255.0)).astype(np.uint8)  # truncation, like tensor.to(torch.uint8)
+    out = inpaint_u8(q, ~(np.asarray(inside_mask) != 0), radius, nthreads)
+    return out.astype(np.float32) / np.float32(255.0)

@@ -155,10 +155,13 @@ def test_accumulate_then_finalize_equals_fused(wr_ctx):
 def test_unsupported_options_raise(wr_ctx):
     mesh, cam, images = _setup(wr_ctx.device)
     proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    with pytest.raises(ValueError):
+        proj(torch.from_numpy(images), mesh, cam, uv_size=64)  # defaults ask for Poisson blending: needs pb_backend
+    with pytest.raises(AssertionError):
+        proj(torch.from_numpy(images), mesh, cam, uv_size=64, poisson_blending=True, uv_padding=False)  # uv.py:427
     with pytest.raises(NotImplementedError):
-        proj(torch.from_numpy(images), mesh, cam, uv_size=64)  # defaults ask for Poisson blending + padding
-    with pytest.raises(NotImplementedError):
-        proj(torch.from_numpy(images), mesh, cam, uv_size=64, poisson_blending=False, uv_padding=True)
+        proj(torch.from_numpy(images), mesh, cam, uv_size=64, poisson_blending=False, uv_padding=False,
+             warp_images=True, images_background=1.0)
 
 
 def test_sharded_bake_single_process_equals_camera_projection(wr_ctx):

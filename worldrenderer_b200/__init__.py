@@ -6,6 +6,7 @@ render / bake path.  Everything that touches pixels or texels runs in hand-writt
 behind the C ABI of include/wr_b200.h (worldrenderer_b200/lib/libwr_b200.so); importing the package
 works without a GPU, calling into it does not.
 """
+from .blend import PoissonBlendingSolver
 from .camera import (
     Camera,
     get_c2w,
@@ -63,5 +64,5 @@ __all__ = [
     "SmartPainter", "get_clip_space_position", "image_to_tensor", "make_image_grid", "tensor_to_image",
     "transform_points_homo", "ExponentialBlend", "RandomChoiceBlend", "SimpleUVValidityStrategy", "UVBlendOutput",
     "UVPrecomputeOutput", "UVRenderAttrOutput", "UVRenderGeometryOutput", "uv_blend", "uv_precompute",
-    "uv_render_attr", "uv_render_geometry",
+    "uv_render_attr", "uv_render_geometry", "PoissonBlendingSolver",
 ]

@@ -23,6 +23,7 @@ SYMBOLS = [
     "wr_status_string", "wr_ctx_last_error", "wr_version", "wr_ctx_create", "wr_ctx_destroy",
     "wr_ctx_scratch_bytes", "wr_ctx_profile", "wr_ctx_profile_read", "wr_ctx_profile_stage_name", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
     "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample", "wr_uv_reduce_finalize_p2p",
+    "wr_poisson_blend", "wr_inpaint_u8", "wr_uv_padding",
 ]
 
 DEPTH_NONE, DEPTH_CONTROLNET, DEPTH_ZERO123PP, DEPTH_SIMPLE = 0, 1, 2, 3
@@ -124,6 +125,12 @@ def lib() -> ctypes.CDLL:
     L.wr_uv_reduce_finalize_p2p.argtypes = [vp, ctypes.POINTER(P2PReduceArgs), vp]
     L.wr_grid_sample.restype = ci
     L.wr_grid_sample.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp, vp]
+    L.wr_poisson_blend.restype = ci
+    L.wr_poisson_blend.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
+    L.wr_inpaint_u8.restype = ci
+    L.wr_inpaint_u8.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
+    L.wr_uv_padding.restype = ci
+    L.wr_uv_padding.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
     _LIB = L
     return L
 
@@ -196,3 +203,19 @@ class NativeContext:
         if n < 0:
             self.check(n, "wr_ctx_profile_read")
         return [(self._lib.wr_ctx_profile_stage_name(self._h, i).decode(), float(buf[i])) for i in range(n)]
+
+
+_DEFAULT_CTX: dict = {}
+
+
+def default_context(device) -> NativeContext:
+    """One shared NativeContext per device for the operators whose reference form takes no context object
+    (cv_ops.inpaint_cvc, uv.uv_padding).  Same rule as everywhere: one stream at a time per context."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"worldrenderer_b200 runs on CUDA devices only (got {dev}); there is no CPU path")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    ctx = _DEFAULT_CTX.get(index)
+    if ctx is None:
+        ctx = _DEFAULT_CTX[index] = NativeContext(torch.device("cuda", index))
+    return ctx

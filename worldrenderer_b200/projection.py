@@ -9,8 +9,10 @@ keyword surface; internally it is four launches groups on one stream:
     unprojection         wr_uv_unproject: per texel, all views, validity, weights, blend, stitch
     (multi-GPU)          accumulators -> all_reduce(SUM) -> wr_uv_finalize      (parallel.py)
 
-Options outside the hot path raise NotImplementedError instead of silently doing something else:
-`poisson_blending=True`, `uv_padding=True`, `warp_images=True`, `remove_bg=True` without a remover.
+    post-processing      wr_uv_padding / wr_poisson_blend (uv.py:426-461) when requested
+
+Options outside the path raise NotImplementedError instead of silently doing something else:
+`warp_images=True`, `remove_bg=True` without a remover.
 """
 from __future__ import annotations
 
@@ -23,7 +25,8 @@ from .camera import Camera, get_camera
 from .mesh import TexturedMesh
 from .render import NVDiffRastContextWrapper
 from .utils import IMAGE_TYPE, LIST_TYPE, image_to_tensor
-from .uv import UVPrecomputeOutput, fused_unproject, fused_view_maps, uv_precompute
+from .blend import PoissonBlendingSolver
+from .uv import UVPrecomputeOutput, atlas_postprocess, fused_unproject, fused_view_maps, uv_precompute
 
 
 @dataclass
@@ -37,10 +40,10 @@ class CameraProjectionOutput:
 class CameraProjection:
     def __init__(self, pb_backend: Optional[str] = None, bg_remover=None, device: str = "cuda",
                  context_type: str = "gl") -> None:
-        # pb_backend selects the reference's Poisson solver backend (blend.py); Poisson blending is
-        # outside this package, the argument is accepted so constructor calls stay source compatible.
+        # pb_backend names the reference's Poisson solver backend (blend.py:186-196); here every backend is the
+        # native kernel.  None (not accepted by the reference) leaves the solver out for callers that never blend.
         self.pb_backend = pb_backend
-        self.pb_solver = None
+        self.pb_solver = PoissonBlendingSolver(pb_backend, device) if pb_backend is not None else None
         self.ctx = NVDiffRastContextWrapper(device, context_type)
         self.bg_remover = bg_remover
         self.device = device
@@ -91,12 +94,9 @@ class CameraProjection:
         return_dict: bool = False,
     ):
         if poisson_blending:
-            raise NotImplementedError("poisson_blending=True needs the Poisson solver (reference blend.py), which is "
-                                      "outside the scope of worldrenderer_b200; pass poisson_blending=False")
-        if uv_padding:
-            raise NotImplementedError("uv_padding=True needs the seam inpainting of the reference (cvcuda, "
-                                      "cv_ops.py), which is outside the scope of worldrenderer_b200; pass "
-                                      "uv_padding=False")
+            assert uv_padding  # uv.py:427
+            if self.pb_solver is None:
+                raise ValueError("poisson_blending=True needs a solver: construct CameraProjection with pb_backend")
         if warp_images:
             raise NotImplementedError("warp_images=True (reference warp.py) is outside the scope of worldrenderer_b200")
 
@@ -143,6 +143,11 @@ class CameraProjection:
             self.ctx, pre, cam, H, W, geo_map, attr_map, view_masks=masks_pt,
             aoi_cos_thresh=aoi_cos_valid_threshold, depth_grad_thresh=depth_grad_threshold,
             alpha=uv_exp_blend_alpha, view_weight=uv_exp_blend_view_weight, want_per_view=return_dict)
+        if poisson_blending or uv_padding:  # uv.py:426-461
+            blend = atlas_postprocess(None, blend, valid_any, pre, do_uv_padding=uv_padding,
+                                      pad_unseen_area=from_scratch, poisson_blending=poisson_blending,
+                                      pb_solver=self.pb_solver, pb_num_iters=pb_num_iters,
+                                      pb_keep_original_border=pb_keep_original_border)
 
         if return_dict:
             return CameraProjectionOutput(uv_proj=blend, uv_proj_mask=valid_any, uv_depth_grad=uv_depth_grad,

@@ -11,8 +11,8 @@ wr_interpolate, wr_render, wr_view_prep, wr_uv_unproject in "materialise" mode, 
 kernel per call that walks the views per texel and never materialises an [Nv,Huv,Wuv,*] tensor
 unless the caller asks for one.
 
-Not provided (outside the hot path): UV seam padding (`uv_padding`, a cvcuda
-inpaint in the reference) and Poisson blending; requesting them raises NotImplementedError.
+Atlas post-processing (SURVEY.md section 8f-2,3): `uv_padding` (seam fill; the reference's cvcuda inpaint is
+replaced by this package's own fill, cv_ops.py) and Poisson blending through `blend.PoissonBlendingSolver`.
 """
 from __future__ import annotations
 
@@ -281,8 +281,20 @@ class RandomChoiceBlend(UVBlendWeightStrategy):
 
 
 def uv_padding(attr: torch.Tensor, inside_mask: torch.Tensor, radius: int):
-    raise NotImplementedError("uv_padding (cvcuda inpaint in the reference, uv.py:373-382) is outside the scope of "
-                              "worldrenderer_b200; call with do_uv_padding=False / uv_padding=False")
+    """Seam padding (uv.py:373-382): clamp to [0,1], quantise like inpaint_cvc (cv_ops.py:23-35), fill the
+    texels outside `inside_mask`.  One `wr_uv_padding` call (clamp + quantise + fill + /255 fused); the fill is
+    this package's own (cv_ops.py docstring), not cvcuda's."""
+    if attr.ndim != 3 or inside_mask.shape != attr.shape[:2]:
+        raise ValueError(f"uv_padding: attr [H,W,C] and inside_mask [H,W] expected, got {tuple(attr.shape)}, "
+                         f"{tuple(inside_mask.shape)}")
+    a = _f32c(attr.detach())
+    m = (inside_mask != 0).contiguous().view(torch.uint8)
+    H, W, C = a.shape
+    out = torch.empty_like(a)
+    c = _native.default_context(a.device)
+    c.check(_native.lib().wr_uv_padding(c.handle, _native.ptr(a), _native.ptr(m), H, W, C, int(radius),
+                                        _native.ptr(out), c.stream()), "wr_uv_padding")
+    return out
 
 
 def uv_blend(
@@ -302,11 +314,8 @@ def uv_blend(
     pb_inplace: bool = False,
     pb_grad_mode: str = "src",
 ) -> UVBlendOutput:
-    """Step-by-step blend on the materialised tensors (uv.py:385-468, non-Poisson branch).  Strategies
-    are arbitrary callables here; the fused path used by CameraProjection is `fused_bake`."""
-    if poisson_blending:
-        raise NotImplementedError("Poisson blending (blend.py) is outside the scope of worldrenderer_b200; "
-                                  "call with poisson_blending=False")
+    """Step-by-step blend on the materialised tensors (uv.py:385-468).  Strategies are arbitrary callables
+    here; the fused path used by CameraProjection is `fused_unproject` followed by `atlas_postprocess`."""
     valid = uv_validity_strategy(uv_precompute_output, uv_render_geometry_output, uv_render_attr_output)
     weight = uv_blend_weight_strategy(uv_precompute_output, uv_render_geometry_output, uv_render_attr_output, valid)
     valid_any = valid.any(dim=0)
@@ -314,12 +323,39 @@ def uv_blend(
         return UVBlendOutput(uv_attr_blend=None, uv_valid_mask=valid, uv_valid_mask_blend=valid_any,
                              uv_blend_weight=weight)
     blend = (uv_render_attr_output.uv_attr_proj * weight[..., None]).sum(axis=0)
-    blend = blend * valid_any[..., None].float() + uv_precompute_output.uv_attr * (~valid_any)[..., None].float()
-    if do_uv_padding:
-        content = valid_any if pad_unseen_area else uv_precompute_output.uv_mask
-        blend = uv_padding(blend, content, uv_padding_radius)
+    stitched = blend * valid_any[..., None].float() + uv_precompute_output.uv_attr * (~valid_any)[..., None].float()
+    blend = atlas_postprocess(blend, stitched, valid_any, uv_precompute_output, do_uv_padding=do_uv_padding,
+                              uv_padding_radius=uv_padding_radius, pad_unseen_area=pad_unseen_area,
+                              poisson_blending=poisson_blending, pb_solver=pb_solver, pb_num_iters=pb_num_iters,
+                              pb_keep_original_border=pb_keep_original_border, pb_inplace=pb_inplace,
+                              pb_grad_mode=pb_grad_mode)
     return UVBlendOutput(uv_attr_blend=blend, uv_valid_mask=valid, uv_valid_mask_blend=valid_any,
                          uv_blend_weight=weight)
+
+
+def atlas_postprocess(blend, stitched, valid_any, pre: UVPrecomputeOutput, *, do_uv_padding=True,
+                      uv_padding_radius=3, pad_unseen_area=False, poisson_blending=False, pb_solver=None,
+                      pb_num_iters=1000, pb_keep_original_border=True, pb_inplace=False, pb_grad_mode="src"):
+    """Tail of uv_blend (uv.py:426-461) shared by the step-by-step and the fused bake: optional Poisson blend of
+    the projected colours into the existing texture, then seam padding.  `blend` is the weighted view sum,
+    `stitched` the same with the existing texture where no view is valid.  Where only texels outside
+    `valid_any` differ (they are refilled by the padding before anything reads them) either may stand in for
+    `blend`, which is how the fused bake calls it with blend=None."""
+    if poisson_blending:
+        assert do_uv_padding  # uv.py:427
+        assert pb_solver is not None
+        padded = uv_padding(stitched if blend is None else blend, valid_any, uv_padding_radius)
+        if pb_keep_original_border:
+            pb_tgt = pre.uv_attr
+        else:
+            pb_tgt = uv_padding(stitched, pre.uv_mask, uv_padding_radius)
+        out = pb_solver(padded, valid_any, pb_tgt, pb_num_iters, inplace=pb_inplace, grad_mode=pb_grad_mode)
+    else:
+        out = stitched
+    if do_uv_padding:
+        content = valid_any if pad_unseen_area else pre.uv_mask
+        out = uv_padding(out, content, uv_padding_radius)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
