@@ -132,11 +132,13 @@ def test_full_size_padding_properties(cuda_device):
     inside[100:900, 50:3000] = True
     inside[2000:2100, 2000:4090] = True
     out = uv_padding(attr, inside, 3)
-    q = (attr.clamp(0, 1) * 255).to(torch.uint8).float() / 255.0
-    assert torch.equal(out[inside], q[inside])
-    assert out.min() >= 0 and out.max() <= 1
+    q8 = (attr.clamp(0, 1) * 255).to(torch.uint8)                 # cv_ops.py:23-24
+    out8 = torch.round(out * 255).to(torch.uint8)
+    assert torch.equal(out8[inside], q8[inside])
+    assert torch.equal(out, out8.float().cpu().div(255.0).to(out.device))  # exactly u8 / 255 (true division)
     again = uv_padding(out, inside, 3)
-    assert torch.equal(again[inside], out[inside])
+    assert torch.equal(again, out)                                # k/255 survives the (x * 255) truncation for every k
+    q = q8.float() / 255.0
     far = out[3500, 100]   # far from every chart: equals an average of known texels, hence inside their range
     assert (far >= q[inside].min()).all() and (far <= q[inside].max()).all()
 
@@ -156,9 +158,9 @@ def _bake_setup(device):
 def test_camera_projection_with_tail(wr_ctx, kw):
     mesh, cam, images = _bake_setup(wr_ctx.device)
     proj = wr.CameraProjection("torch-cuda", None, str(wr_ctx.device), "cuda")
-    common = dict(uv_size=128, iou_rejection_threshold=None, aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
+    common = dict(iou_rejection_threshold=None, aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1,
                   uv_exp_blend_alpha=3.0)
-    out, valid = proj(torch.from_numpy(images), mesh, cam, return_uv_projection_mask=True, **common, **kw)
+    out, valid = proj(torch.from_numpy(images), mesh, cam, uv_size=128, return_uv_projection_mask=True, **common, **kw)
     n32 = lambda t: t.cpu().numpy().astype(np.int32)
     ref = render_oracle.camera_projection(
         images, mesh.v_pos.cpu().numpy(), n32(mesh.t_pos_idx), mesh.v_nrm.cpu().numpy(), n32(mesh.t_pos_idx),

@@ -15,6 +15,7 @@ from worldrenderer_b200 import synth  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--per-view", action="store_true")
+ap.add_argument("--quick", action="store_true", help="with --per-view: only the all-views table")
 ap.add_argument("--bake", action="store_true")
 ap.add_argument("--mesh", default="terrain")
 ap.add_argument("--depth", default="controlnet")
@@ -57,8 +58,8 @@ for _ in range(args.steps):
     out = wr.render(ctx, mesh, cam, 768, 768, render_attr=False, depth_normalization_strategy=STRAT)
 torch.cuda.synchronize()
 if args.per_view:
-    print("all views (us):", {k: round(x, 1) for k, x in stage_table(cam, 10).items()})
-    for b in range(6):
+    print("all views (us):", {k: round(x, 1) for k, x in stage_table(cam, 30).items()})
+    for b in range(0 if args.quick else 6):
         t = stage_table(cam[b], 10)
         print(f"view {b} covered={int(out.mask[b].sum())} (us):", {k: round(x, 1) for k, x in t.items()})
 if args.bake:

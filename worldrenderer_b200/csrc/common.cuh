@@ -103,10 +103,25 @@ struct RasterResult {
 // buffer is known clean again and the next call can skip the clear.
 static inline void wr_raster_consumed(wr_ctx *ctx, const RasterResult *res) { ctx->clean_bytes = res->packed_bytes; }
 
+// Optional by-product of the vertex pass of a fused render: 16-byte records of the world positions and the
+// normals, so that the shading kernel gathers one LDG.128 per vertex attribute instead of three LDG.32.
+struct VertexPack {
+    const float *v_nrm;   // in: [Vn,3] or nullptr
+    int Vn;               // in
+    size_t offset;        // in: byte offset of the records inside the extra scratch (256-byte aligned)
+    float4 *pos4;         // out: [V]  (x, y, z, 0)
+    float4 *nrm4;         // out: [Vn] (x, y, z, 0), nullptr without normals
+};
+static inline size_t wr_vertex_pack_bytes(int V, int Vn, bool normals)
+{
+    return (((size_t)(V > 0 ? V : 1) * 16 + 255) & ~(size_t)255) + (normals ? (size_t)(Vn > 0 ? Vn : 1) * 16 : 0);
+}
+
 int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream);
 int wr_set_cuda_error(wr_ctx *ctx, cudaError_t e, const char *where);
 int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
-                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream);
+                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream,
+                  VertexPack *pack = nullptr);
 
 #define WR_CHECK_LAUNCH(ctx, where)                                  \
     do {                                                             \

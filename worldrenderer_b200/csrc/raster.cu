@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
 
 // All views of a vertex in one thread: the position is read once, B independent snap chains.
 __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int B, int W, int H, SnapVert *sv,
-                                                                int *stats, int nstats)
+                                                                int *stats, int nstats, VertexPack pack)
 {
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
@@ -228,9 +228,14 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
         s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pack.nrm4 && v < pack.Vn) {
+        const float *n = pack.v_nrm + 3 * (size_t)v;
+        pack.nrm4[v] = make_float4(__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f);
+    }
     if (v >= src.V) return;
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
     for (int b = 0; b < B; ++b) {
         float4 r0, r1, r2, r3;
         if (b < kStageViews) {
@@ -542,7 +547,8 @@ __global__ void __launch_bounds__(256) k_resolve_rast(unsigned long long *packed
 // Runs snap -> setup -> queue rasterisation into the context scratch.  `extra_bytes` of additional
 // scratch are reserved behind the raster buffers and returned through `extra`.
 int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
-                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream)
+                  int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream,
+                  VertexPack *pack)
 {
     const int V = src.V;
     const size_t sv_bytes = wr_align256((size_t)B * (size_t)(V > 0 ? V : 1) * sizeof(SnapVert));
@@ -558,7 +564,16 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
     SnapVert *sv = reinterpret_cast<SnapVert *>(base + depth_bytes);
     uint32_t *queue = reinterpret_cast<uint32_t *>(base + sv_bytes + depth_bytes);
     int *stats = reinterpret_cast<int *>(base + sv_bytes + depth_bytes + queue_bytes);  // [B,4] counters + [B,4] user
-    if (extra) *extra = base + sv_bytes + depth_bytes + queue_bytes + stats_bytes;
+    char *extra_base = base + sv_bytes + depth_bytes + queue_bytes + stats_bytes;
+    if (extra) *extra = extra_base;
+    VertexPack vp;
+    vp.v_nrm = nullptr; vp.Vn = 0; vp.offset = 0; vp.pos4 = nullptr; vp.nrm4 = nullptr;
+    if (pack) {
+        pack->pos4 = reinterpret_cast<float4 *>(extra_base + pack->offset);
+        pack->nrm4 = pack->v_nrm ? reinterpret_cast<float4 *>(extra_base + pack->offset + wr_align256((size_t)(V > 0 ? V : 1) * 16))
+                                 : nullptr;
+        vp = *pack;
+    }
 
     wr_stage(ctx, stream, "clear");
     const size_t packed_bytes = (size_t)B * H * W * sizeof(unsigned long long);
@@ -584,7 +599,8 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         const int qgrid = ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
         if (src.mvp)
-            k_snap_vertices_allviews<<<wr_div_up(V, 256), 256, 0, stream>>>(src, B, W, H, sv, stats, B * 8);
+            k_snap_vertices_allviews<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
+                src, B, W, H, sv, stats, B * 8, vp);
         else
             k_snap_vertices<<<dim3(wr_div_up(V, 256), B), 256, 0, stream>>>(src, 0, W, H, sv, stats, B * 8);
         WR_CHECK_LAUNCH(ctx, "k_snap_vertices");

@@ -25,6 +25,11 @@ struct ShadeParams {
     uint8_t *mask;               // [B,H,W] coverage: the caller's out_mask or scratch
     uint32_t *range;             // [B,4] zero-initialised: [0] = max of ~ordered(d) over all pixels (i.e. the
                                  // minimum), [1] = max of ordered(d) over covered pixels (0 = none)
+    const float4 *pos4;          // [V]  (x, y, z, 0) written by the vertex pass
+    const float4 *nrm4;          // [Vn] (x, y, z, 0) or nullptr
+    int wide_ok;                 // W % 4 == 0 and 16-byte aligned pos / normal maps: background rows may use 16-byte stores
+    int bg_final;                // two-pass depth whose background value is a constant (controlnet, zero123++):
+                                 // written here, k_depth_finalize then only touches covered pixels
 };
 
 struct PixelGeo {
@@ -56,32 +61,66 @@ __device__ __forceinline__ float apply_simple(float d, float scale, float offset
 }
 
 // Everything render() derives for a covered pixel (c, r) won by triangle `id`.  m = mvp of the view.
-__device__ __forceinline__ void shade_covered(const wr_render_args &A, const float *m, int id, int c, int r,
-                                              bool want_normal, bool want_zw, bool want_tangent, PixelGeo &g)
+// The three world positions and normals of a triangle: one 16-byte gather each from the records the vertex
+// pass left in scratch (L2-resident).
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 ld3(const float4 *p)
 {
-    const int W = A.W, H = A.H;
-    const int i0 = __ldg(A.tri + 3 * (size_t)id), i1 = __ldg(A.tri + 3 * (size_t)id + 1),
-              i2 = __ldg(A.tri + 3 * (size_t)id + 2);
-    const float *q0 = A.v_pos + 3 * (size_t)i0, *q1 = A.v_pos + 3 * (size_t)i1, *q2 = A.v_pos + 3 * (size_t)i2;
-    const float x0 = __ldg(q0), y0 = __ldg(q0 + 1), z0 = __ldg(q0 + 2);
-    const float x1 = __ldg(q1), y1 = __ldg(q1 + 1), z1 = __ldg(q1 + 2);
-    const float x2 = __ldg(q2), y2 = __ldg(q2 + 1), z2 = __ldg(q2 + 2);
-    // the normal gathers depend on the indices only: issue them with the position gathers so that both
-    // round trips overlap (and overlap the barycentric math below)
-    float n0x = 0.f, n0y = 0.f, n0z = 0.f, n1x = 0.f, n1y = 0.f, n1z = 0.f, n2x = 0.f, n2y = 0.f, n2z = 0.f;
+    const float4 t = __ldg(p);
+    V3 r; r.x = t.x; r.y = t.y; r.z = t.z;
+    return r;
+}
+struct TriVerts {
+    V3 q0, q1, q2, n0, n1, n2;
+};
+struct TriIdx {
+    int i0, i1, i2;
+};
+
+__device__ __forceinline__ TriIdx load_tri_idx(const wr_render_args &A, int id)
+{
+    TriIdx t;
+    t.i0 = __ldg(A.tri + 3 * (size_t)id); t.i1 = __ldg(A.tri + 3 * (size_t)id + 1); t.i2 = __ldg(A.tri + 3 * (size_t)id + 2);
+    return t;
+}
+
+// the normal gathers depend on the indices only: they are issued with the position gathers so that both round
+// trips overlap
+__device__ __forceinline__ TriVerts gather_tri(const wr_render_args &A, const float4 *pos4, const float4 *nrm4, int id,
+                                               const TriIdx &t, bool want_normal)
+{
+    TriVerts v;
+    v.q0 = ld3(pos4 + t.i0); v.q1 = ld3(pos4 + t.i1); v.q2 = ld3(pos4 + t.i2);
+    v.n0.x = v.n0.y = v.n0.z = 0.f;
+    v.n1 = v.n0; v.n2 = v.n0;
     if (want_normal) {
-        int j0 = i0, j1 = i1, j2 = i2;
+        int j0 = t.i0, j1 = t.i1, j2 = t.i2;
         if (A.tri_nrm) {
             j0 = __ldg(A.tri_nrm + 3 * (size_t)id); j1 = __ldg(A.tri_nrm + 3 * (size_t)id + 1);
             j2 = __ldg(A.tri_nrm + 3 * (size_t)id + 2);
         }
         if ((unsigned)j0 < (unsigned)A.Vn && (unsigned)j1 < (unsigned)A.Vn && (unsigned)j2 < (unsigned)A.Vn) {
-            const float *n0 = A.v_nrm + 3 * (size_t)j0, *n1 = A.v_nrm + 3 * (size_t)j1, *n2 = A.v_nrm + 3 * (size_t)j2;
-            n0x = __ldg(n0); n0y = __ldg(n0 + 1); n0z = __ldg(n0 + 2);
-            n1x = __ldg(n1); n1y = __ldg(n1 + 1); n1z = __ldg(n1 + 2);
-            n2x = __ldg(n2); n2y = __ldg(n2 + 1); n2z = __ldg(n2 + 2);
+            v.n0 = ld3(nrm4 + j0); v.n1 = ld3(nrm4 + j1); v.n2 = ld3(nrm4 + j2);
         }
     }
+    return v;
+}
+
+// Everything render() derives for a covered pixel (c, r) won by triangle `id`.  m = mvp of the view.
+__device__ __forceinline__ void shade_covered(const wr_render_args &A, const TriVerts &tv, const TriIdx &ti,
+                                              const float *m, int id, int c, int r, bool want_normal, bool want_zw,
+                                              bool want_tangent, PixelGeo &g)
+{
+    const int W = A.W, H = A.H;
+    const int i0 = ti.i0, i1 = ti.i1, i2 = ti.i2;
+    const float x0 = tv.q0.x, y0 = tv.q0.y, z0 = tv.q0.z;
+    const float x1 = tv.q1.x, y1 = tv.q1.y, z1 = tv.q1.z;
+    const float x2 = tv.q2.x, y2 = tv.q2.y, z2 = tv.q2.z;
+    const float n0x = tv.n0.x, n0y = tv.n0.y, n0z = tv.n0.z;
+    const float n1x = tv.n1.x, n1y = tv.n1.y, n1z = tv.n1.z;
+    const float n2x = tv.n2.x, n2y = tv.n2.y, n2z = tv.n2.z;
     // clip-space vertices, utils.py:127-129 in the contract's operation order
     const float c0x = ((m[0] * x0 + m[1] * y0) + m[2] * z0) + m[3];
     const float c0y = ((m[4] * x0 + m[5] * y0) + m[6] * z0) + m[7];
@@ -145,7 +184,16 @@ __device__ __forceinline__ void shade_covered(const wr_render_args &A, const flo
     }
 }
 
-constexpr int kShadeRows = 4;  // rows per thread: four independent 8-byte loads in flight before any use
+#ifndef WR_SHADE_ROWS
+#define WR_SHADE_ROWS 4
+#endif
+#ifndef WR_SHADE_MINB
+#define WR_SHADE_MINB 8   // 64 registers: measured 47.3 us vs 49.6 us unconstrained on config B
+#endif
+#ifndef WR_SHADE_PIPE
+#define WR_SHADE_PIPE 0
+#endif
+constexpr int kShadeRows = WR_SHADE_ROWS;  // rows per thread: that many independent id loads in flight before any use
 
 // Output sets with their own instantiation (no per-pixel pointer tests, ~30% fewer issued instructions on
 // config B); every other combination runs the generic instantiation (OUTS < 0, runtime tests).
@@ -156,7 +204,7 @@ constexpr int kOutsBakeView = kOutGeo | kOutDepth;                        // mas
 
 // One column strip of kShadeRows pixels per thread.  grid = (ceil(W/128), ceil(H/kShadeRows), B), 128 threads.
 template <int OUTS>
-__global__ void __launch_bounds__(128) k_shade(ShadeParams P)
+__global__ void __launch_bounds__(128, WR_SHADE_MINB) k_shade(ShadeParams P)
 {
     const wr_render_args &A = P.a;
     constexpr bool kGeneric = OUTS < 0;
@@ -178,32 +226,33 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
     const int W = A.W, H = A.H;
     const bool live = c < W;
 
-    // Per-block depth range in shared memory.  The only block barrier sits at kernel entry, where no warp
-    // waits on memory yet; afterwards warps retire independently and the last one to finish publishes --
-    // and only if the block improves on the range it saw at entry (after the first wave almost none does).
-    __shared__ uint32_t s_lo, s_hi, s_done, s_seen_lo, s_seen_hi;
-    if (two_pass) {
-        if (threadIdx.x == 0) {
-            s_lo = 0u; s_hi = 0u; s_done = 0u;
-            s_seen_lo = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b);
-            s_seen_hi = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b + 1);
-        }
-        __syncthreads();
-    }
-
     const size_t o0 = ((size_t)b * H + r0) * W + (live ? c : 0);
     const int nrows = live ? min(kShadeRows, H - r0) : 0;
-    unsigned long long pk[kShadeRows];
+    // Only the low word (triangle id; 0xFFFFFFFF = empty) of each packed entry is needed: four 4-byte loads in
+    // flight per thread, issued before anything else so that the block prologue below overlaps their latency.
+    const uint32_t *pk32 = reinterpret_cast<const uint32_t *>(P.packed);
+    uint32_t idw[kShadeRows];
 #pragma unroll
-    for (int k = 0; k < kShadeRows; ++k) pk[k] = (k < nrows) ? P.packed[o0 + (size_t)k * W] : WR_EMPTY_PIXEL;
-    float m[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) m[j] = __ldg(A.mvp + 16 * b + j);  // independent of the packed ids: in flight with them
-    float wz0 = 0.f, wz1 = 0.f, wz2 = 0.f, wz3 = 0.f;
-    if (has_depth) {
-        const float *m2 = A.w2c + 16 * b + 8;
-        wz0 = __ldg(m2); wz1 = __ldg(m2 + 1); wz2 = __ldg(m2 + 2); wz3 = __ldg(m2 + 3);
+    for (int k = 0; k < kShadeRows; ++k) idw[k] = (k < nrows) ? pk32[2 * (o0 + (size_t)k * W)] : 0xFFFFFFFFu;
+
+    // Block prologue: the view's matrices go to shared memory (read back as broadcasts in the covered path, which
+    // keeps 20 registers free), and the per-block depth range is initialised.  This is the only block barrier;
+    // afterwards warps retire independently and the last one to finish publishes the block's range -- and only
+    // if it improves on the range seen at entry (after the first wave almost none does).
+    __shared__ float s_m[16];
+    __shared__ float s_wz[4];
+    __shared__ uint32_t s_lo, s_hi, s_done, s_seen_lo, s_seen_hi;
+    if (threadIdx.x < 16) s_m[threadIdx.x] = __ldg(A.mvp + 16 * b + threadIdx.x);
+    if (has_depth && threadIdx.x >= 32 && threadIdx.x < 36) s_wz[threadIdx.x - 32] = __ldg(A.w2c + 16 * b + 8 + (threadIdx.x - 32));
+    if (two_pass && threadIdx.x == 64) {
+        s_lo = 0u; s_hi = 0u; s_done = 0u;
+        s_seen_lo = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b);
+        s_seen_hi = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b + 1);
     }
+    __syncthreads();
+    const float *m = s_m;
+    float wz0 = 0.f, wz1 = 0.f, wz2 = 0.f, wz3 = 0.f;
+    if (has_depth) { wz0 = s_wz[0]; wz1 = s_wz[1]; wz2 = s_wz[2]; wz3 = s_wz[3]; }
     const float nbx = A.normal_bg[0], nby = A.normal_bg[1], nbz = A.normal_bg[2];
     float rot[9];
     if (has_geo) {
@@ -211,12 +260,77 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
         for (int j = 0; j < 9; ++j) rot[j] = __ldg(A.w2c + 16 * b + 4 * (j / 3) + (j % 3));  // R = w2c[:3,:3]
     }
     float lo = INFINITY, hi = -INFINITY;
+    const bool bg_final = two_pass && P.bg_final;
 
+    // Strip without a covered pixel in the whole warp (78% of the warps of config B): every lane writes the same
+    // constants, so position and normal rows go out as 24 full 16-byte stores each instead of 2 x 3 strided
+    // 4-byte stores per lane.  Only the specialised instantiations take it (their output set is known).
+    if (!kGeneric && !has_geo && P.wide_ok) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kShadeRows; ++k) any |= idw[k] != 0xFFFFFFFFu;
+        const unsigned lane = threadIdx.x & 31;
+        const int cw = c - (int)lane;  // first column of the warp
+        if (__ballot_sync(0xFFFFFFFFu, any) == 0 && cw + 32 <= W) {
+            const float d_bg = -(((wz0 * 0.0f + wz1 * 0.0f) + wz2 * 0.0f) + wz3);
+            float4 n4;  // elements 4*lane .. 4*lane+3 of the repeating (nbx, nby, nbz) row
+            {
+                const int e = (4 * (int)lane) % 3;
+                const float t0 = e == 0 ? nbx : (e == 1 ? nby : nbz);
+                const float t1 = e == 0 ? nby : (e == 1 ? nbz : nbx);
+                const float t2 = e == 0 ? nbz : (e == 1 ? nbx : nby);
+                n4 = make_float4(t0, t1, t2, t0);
+            }
+            for (int k = 0; k < nrows; ++k) {
+                const size_t o = o0 + (size_t)k * W;
+                const size_t row4 = (3 * (o - lane)) >> 2;  // float4 index of the warp's row segment
+                if (lane < 24) {
+                    reinterpret_cast<float4 *>(A.out_pos)[row4 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_normal) reinterpret_cast<float4 *>(A.out_normal)[row4 + lane] = n4;
+                }
+                P.mask[o] = 0;
+                if (has_depth) A.out_depth[o] = two_pass ? (bg_final ? A.depth_bg : d_bg) : A.depth_bg;
+            }
+            if (two_pass) lo = d_bg;
+            goto publish;
+        }
+    }
+
+    // Covered pixels need two dependent gathers (id -> vertex indices -> vertex records).  Walking the strip row by
+    // row would serialise 2 x rows round trips per thread, so (WR_SHADE_PIPE >= 1) the index loads of all rows are
+    // issued together, and (>= 2) the vertex records of row k+1 are requested before row k is shaded.
+#if WR_SHADE_PIPE >= 1
+    TriIdx tix[kShadeRows];
+#pragma unroll
+    for (int k = 0; k < kShadeRows; ++k) {
+        tix[k].i0 = tix[k].i1 = tix[k].i2 = 0;
+        if (idw[k] != 0xFFFFFFFFu) tix[k] = load_tri_idx(A, (int)idw[k]);
+    }
+#endif
+#if WR_SHADE_PIPE >= 2
+    TriVerts tv_next;
+    tv_next.q0.x = tv_next.q0.y = tv_next.q0.z = 0.f;
+    tv_next.q1 = tv_next.q2 = tv_next.n0 = tv_next.n1 = tv_next.n2 = tv_next.q0;
+    if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
+#endif
 #pragma unroll 1
     for (int k = 0; k < nrows; ++k) {
         const int r = r0 + k;
         const size_t o = o0 + (size_t)k * W;
-        const bool covered = pk[k] != WR_EMPTY_PIXEL;
+        const uint32_t idk = idw[0];
+#pragma unroll
+        for (int j = 0; j + 1 < kShadeRows; ++j) idw[j] = idw[j + 1];  // register rotation: no indexed local array
+        idw[kShadeRows - 1] = 0xFFFFFFFFu;
+#if WR_SHADE_PIPE >= 1
+        const TriIdx tik = tix[0];
+#pragma unroll
+        for (int j = 0; j + 1 < kShadeRows; ++j) tix[j] = tix[j + 1];
+#endif
+#if WR_SHADE_PIPE >= 2
+        const TriVerts tvk = tv_next;
+        if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
+#endif
+        const bool covered = idk != 0xFFFFFFFFu;
         int id = -1;
         PixelGeo g;
         g.px = g.py = g.pz = 0.f;
@@ -225,8 +339,14 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
         g.u = g.v = g.w = 0.f; g.zw = 0.f;
         if (covered) {
             P.packed[o] = WR_EMPTY_PIXEL;  // self-cleaning
-            id = (int)(uint32_t)(pk[k] & 0xFFFFFFFFull);
-            shade_covered(A, m, id, c, r, need_normal, has_rast, has_tangent, g);
+            id = (int)idk;
+#if WR_SHADE_PIPE == 0
+            const TriIdx tik = load_tri_idx(A, id);
+#endif
+#if WR_SHADE_PIPE < 2
+            const TriVerts tvk = gather_tri(A, P.pos4, P.nrm4, id, tik, need_normal);
+#endif
+            shade_covered(A, tvk, tik, m, id, c, r, need_normal, has_rast, has_tangent, g);
         }
         if (has_mask) P.mask[o] = covered ? 1 : 0;
         if (has_geo) {
@@ -277,13 +397,14 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
             if (!two_pass) {
                 A.out_depth[o] = covered ? apply_simple(d, A.depth_p0, A.depth_p1, A.depth_clamp) : A.depth_bg;
             } else {
-                A.out_depth[o] = d;
+                A.out_depth[o] = (bg_final && !covered) ? A.depth_bg : d;
                 lo = fminf(lo, d);
                 if (covered) hi = fmaxf(hi, d);
             }
         }
     }
 
+publish:
     if (two_pass) {
         // per-view (min over all pixels, max over covered pixels): warp shuffle -> shared atomics -> the
         // last warp of the block issues at most one global atomic pair
@@ -305,11 +426,9 @@ __global__ void __launch_bounds__(128) k_shade(ShadeParams P)
     }
 }
 
-// Second depth pass (render.py:250-257): background <- per-view min, then the normaliser.
-// kFinGroups x 4 pixels per thread; the groups of a thread are a block-stride apart so every load
-// instruction stays coalesced and all of a thread's loads are in flight together.
-constexpr int kFinGroups = 1;
-
+// Second depth pass (render.py:250-257): background <- per-view min, then the normaliser.  Four pixels per
+// thread.  When the shading kernel already wrote the constant background value (bg_final) a group without a
+// covered pixel is skipped after its 4-byte mask load -- on config B that is three quarters of the groups.
 __device__ __forceinline__ float finalize_one(float d, bool covered, float lo, float den, int mode, float p0, float p1,
                                               float bg)
 {
@@ -328,45 +447,35 @@ __device__ __forceinline__ float finalize_one(float d, bool covered, float lo, f
 
 __global__ void __launch_bounds__(256) k_depth_finalize(float *depth, const uint8_t *mask, const uint32_t *range,
                                                         long long npix_view, int mode, float p0, float p1, float bg,
-                                                        int vec)
+                                                        int vec, int bg_final)
 {
     const int b = blockIdx.y;
-    const float lo = wr_ordered_float(~range[4 * b]);
-    const uint32_t hik = range[4 * b + 1];
-    const float hi = hik == 0u ? lo : wr_ordered_float(hik);  // no covered pixel: filled image is constant lo
-    const float den = (hi - lo) + 1e-5f;
     float *dv = depth + (size_t)b * npix_view;
     const uint8_t *mv = mask + (size_t)b * npix_view;
-    const long long base = (long long)blockIdx.x * (256 * kFinGroups) + threadIdx.x;  // group index
+    const long long gi = (long long)blockIdx.x * 256 + threadIdx.x;  // group of 4 pixels
     if (vec) {
-        const long long ngroups = npix_view >> 2;
-        float4 d[kFinGroups];
-        uchar4 m[kFinGroups];
-#pragma unroll
-        for (int k = 0; k < kFinGroups; ++k) {
-            const long long gi = base + 256 * k;
-            if (gi < ngroups) {
-                d[k] = reinterpret_cast<const float4 *>(dv)[gi];
-                m[k] = reinterpret_cast<const uchar4 *>(mv)[gi];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kFinGroups; ++k) {
-            const long long gi = base + 256 * k;
-            if (gi < ngroups) {
-                float4 o;
-                o.x = finalize_one(d[k].x, m[k].x, lo, den, mode, p0, p1, bg);
-                o.y = finalize_one(d[k].y, m[k].y, lo, den, mode, p0, p1, bg);
-                o.z = finalize_one(d[k].z, m[k].z, lo, den, mode, p0, p1, bg);
-                o.w = finalize_one(d[k].w, m[k].w, lo, den, mode, p0, p1, bg);
-                reinterpret_cast<float4 *>(dv)[gi] = o;
-            }
-        }
+        if (gi >= (npix_view >> 2)) return;
+        const uchar4 m = reinterpret_cast<const uchar4 *>(mv)[gi];
+        if (bg_final && !(m.x | m.y | m.z | m.w)) return;
+        const float4 d = reinterpret_cast<const float4 *>(dv)[gi];
+        const float lo = wr_ordered_float(~range[4 * b]);
+        const uint32_t hik = range[4 * b + 1];
+        const float hi = hik == 0u ? lo : wr_ordered_float(hik);  // no covered pixel: filled image is constant lo
+        const float den = (hi - lo) + 1e-5f;
+        float4 o;
+        o.x = finalize_one(d.x, m.x, lo, den, mode, p0, p1, bg);
+        o.y = finalize_one(d.y, m.y, lo, den, mode, p0, p1, bg);
+        o.z = finalize_one(d.z, m.z, lo, den, mode, p0, p1, bg);
+        o.w = finalize_one(d.w, m.w, lo, den, mode, p0, p1, bg);
+        reinterpret_cast<float4 *>(dv)[gi] = o;
     } else {
-        for (int k = 0; k < kFinGroups; ++k) {
-            const long long i0 = (base + 256 * k) * 4;
-            for (int j = 0; j < 4; ++j)
-                if (i0 + j < npix_view) dv[i0 + j] = finalize_one(dv[i0 + j], mv[i0 + j] != 0, lo, den, mode, p0, p1, bg);
+        const float lo = wr_ordered_float(~range[4 * b]);
+        const uint32_t hik = range[4 * b + 1];
+        const float hi = hik == 0u ? lo : wr_ordered_float(hik);
+        const float den = (hi - lo) + 1e-5f;
+        for (int j = 0; j < 4; ++j) {
+            const long long i = gi * 4 + j;
+            if (i < npix_view) dv[i] = finalize_one(dv[i], mv[i] != 0, lo, den, mode, p0, p1, bg);
         }
     }
 }
@@ -400,8 +509,14 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     const size_t npix = (size_t)A.B * A.H * A.W;
     void *extra = nullptr;
     wr_stage_begin(ctx);
-    int rc = wr_run_raster(ctx, src, A.B, A.tri, A.F, nullptr, A.H, A.W, (two_pass && !A.out_mask) ? npix : 0, &res,
-                           &extra, stream);
+    const size_t mask_bytes = (two_pass && !A.out_mask) ? wr_align256(npix) : 0;
+    const bool want_nrm = A.v_nrm && (A.out_normal || A.out_geo);
+    VertexPack pack;
+    pack.v_nrm = want_nrm ? A.v_nrm : nullptr;
+    pack.Vn = A.Vn;
+    pack.offset = mask_bytes;
+    int rc = wr_run_raster(ctx, src, A.B, A.tri, A.F, nullptr, A.H, A.W,
+                           mask_bytes + wr_vertex_pack_bytes(A.V, A.Vn, want_nrm), &res, &extra, stream, &pack);
     if (rc != WR_OK) return rc;
 
     ShadeParams P;
@@ -409,6 +524,11 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     P.packed = res.packed;
     P.mask = A.out_mask ? A.out_mask : (two_pass ? static_cast<uint8_t *>(extra) : nullptr);
     P.range = reinterpret_cast<uint32_t *>(res.view_stats);
+    P.pos4 = pack.pos4;
+    P.nrm4 = pack.nrm4;
+    P.wide_ok = (A.W & 3) == 0 && (reinterpret_cast<uintptr_t>(A.out_pos) & 15u) == 0 &&
+                (reinterpret_cast<uintptr_t>(A.out_normal) & 15u) == 0;
+    P.bg_final = two_pass && (A.depth_mode == WR_DEPTH_CONTROLNET || A.depth_mode == WR_DEPTH_ZERO123PP);
     wr_stage(ctx, stream, "k_shade");
     {
         const dim3 grid(wr_div_up(A.W, 128), wr_div_up(A.H, kShadeRows), A.B);
@@ -427,8 +547,8 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
         const int vec = (npv & 3) == 0 && (reinterpret_cast<uintptr_t>(A.out_depth) & 15u) == 0 &&
                         (reinterpret_cast<uintptr_t>(P.mask) & 3u) == 0;
         wr_stage(ctx, stream, "k_depth_finalize");
-        k_depth_finalize<<<dim3(wr_div_up(wr_div_up(npv, 4), 256 * kFinGroups), A.B), 256, 0, stream>>>(
-            A.out_depth, P.mask, P.range, npv, A.depth_mode, A.depth_p0, A.depth_p1, A.depth_bg, vec);
+        k_depth_finalize<<<dim3(wr_div_up(wr_div_up(npv, 4), 256), A.B), 256, 0, stream>>>(
+            A.out_depth, P.mask, P.range, npv, A.depth_mode, A.depth_p0, A.depth_p1, A.depth_bg, vec, P.bg_final);
         WR_CHECK_LAUNCH(ctx, "k_depth_finalize");
     }
     wr_stage(ctx, stream, "end");
