@@ -123,6 +123,47 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
                   int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream,
                   VertexPack *pack = nullptr);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while its
+// predecessor on the stream is still draining; it must execute wr_pdl_wait() before touching anything the
+// predecessor wrote (the wait also covers the predecessor's predecessors, every kernel of the chain waits
+// first thing).  wr_pdl_trigger() in the predecessor allows the dependent's blocks to be placed as soon as all
+// of the predecessor's blocks have been issued.  Used to hide the launch latency between the five short kernels
+// of a render step; disabled while per-stage events are being recorded.
+#ifndef WR_PDL
+#define WR_PDL 1
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ void wr_pdl_wait()
+{
+#if WR_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void wr_pdl_trigger()
+{
+#if WR_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline void wr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool dependent,
+                             Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (WR_PDL && dependent) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through WR_CHECK_LAUNCH
+}
+
 #define WR_CHECK_LAUNCH(ctx, where)                                  \
     do {                                                             \
         cudaError_t e__ = cudaGetLastError();                        \

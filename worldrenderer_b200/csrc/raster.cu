@@ -149,6 +149,8 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
 // not by divergence; see profiles/README.md.)
 __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0)
 {
+    wr_pdl_wait();
+    wr_pdl_trigger();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + view0;
     const int W = P.W, H = P.H;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
 __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int B, int W, int H, SnapVert *sv,
                                                                 int *stats, int nstats, VertexPack pack)
 {
+    wr_pdl_trigger();
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
     // the B view matrices are staged in shared memory once per block (16-byte broadcast reads instead of 16
@@ -497,6 +500,8 @@ __device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc
 __global__ void __launch_bounds__(256) k_raster_queues(RasterParams P, VtxSrc src, int view0)
 {
     __shared__ WarpClipScratch clip_smem[8];
+    wr_pdl_wait();
+    wr_pdl_trigger();
     const int b = blockIdx.y + view0;
     raster_queue<false>(P, src, b, clip_smem);
     raster_queue<true>(P, src, b, clip_smem);
@@ -606,10 +611,11 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         WR_CHECK_LAUNCH(ctx, "k_snap_vertices");
         if (!tri_ranges) {
             wr_stage(ctx, stream, "k_setup_triangles");
-            k_setup_triangles<<<dim3(wr_div_up(F, 256), B), 256, 0, stream>>>(P, 0);
+            const bool pdl = !ctx->profiling && src.mvp != nullptr;  // the chain starts at k_snap_vertices_allviews
+            wr_launch(k_setup_triangles, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0);
             WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
             wr_stage(ctx, stream, "k_raster_queues");
-            k_raster_queues<<<dim3(qgrid, B), 256, 0, stream>>>(P, src, 0);
+            wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);
             WR_CHECK_LAUNCH(ctx, "k_raster_queues");
         } else {
             for (int b = 0; b < B; ++b) {
