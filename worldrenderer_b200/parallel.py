@@ -187,15 +187,21 @@ def _uv_precompute_cached(ctx, mesh, uv_size: int):
 def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_size: int, *, view_masks_local=None,
                  aoi_cos_valid_threshold: float = 0.3, depth_grad_dilation: int = 5,
                  depth_grad_threshold: Optional[float] = 0.1, uv_exp_blend_alpha: float = 6.0,
-                 uv_exp_blend_view_weight_local=None, group=None, exchange: str = "auto"):
+                 uv_exp_blend_view_weight_local=None, group=None, exchange: str = "auto",
+                 uv_padding: bool = False, poisson_blending: bool = False, pb_solver=None, pb_num_iters: int = 1000,
+                 pb_keep_original_border: bool = True, from_scratch: bool = False):
     """Config E: this rank holds `cam_local` / `images_local` (its share of the views, possibly none);
     the mesh is replicated.  Returns (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on all ranks.
 
     exchange: "p2p"  -- one fused kernel over NVLink peer memory (reduce-scatter + finalise + all-gather);
               "nccl" -- all_reduce(SUM) of the accumulators, then wr_uv_finalize on every rank;
               "auto" -- p2p when symmetric memory is available for the group, else nccl.
-    With "p2p" / "auto" the returned tensors are views of the workspace: valid until the next bake of that size."""
-    from .uv import fused_unproject, fused_view_maps, uv_finalize
+    With "p2p" / "auto" the returned tensors are views of the workspace: valid until the next bake of that size.
+
+    uv_padding / poisson_blending: the post-processing tail of uv_blend (uv.py:426-461) applied to the exchanged
+    atlas.  It is deterministic and cheap next to the exchange, so every rank runs it on its own copy (no second
+    collective); the returned atlas is then a fresh tensor, still identical on all ranks."""
+    from .uv import atlas_postprocess, fused_unproject, fused_view_maps, uv_finalize
     if exchange not in ("auto", "p2p", "nccl"):
         raise ValueError(f"exchange={exchange!r}")
     pre = _uv_precompute_cached(ctx, mesh, uv_size)
@@ -216,6 +222,12 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
     else:
         accum = torch.zeros((uv_size, uv_size, 5), dtype=torch.float32, device=ctx.device)
     if ws is not None:
-        return ws.reduce_finalize(ctx, pre.uv_attr)
-    all_reduce_accumulators(accum, group)
-    return uv_finalize(ctx, accum, pre.uv_attr)
+        atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr)
+    else:
+        all_reduce_accumulators(accum, group)
+        atlas, valid_any = uv_finalize(ctx, accum, pre.uv_attr)
+    if uv_padding or poisson_blending:
+        atlas = atlas_postprocess(None, atlas, valid_any, pre, do_uv_padding=uv_padding, pad_unseen_area=from_scratch,
+                                  poisson_blending=poisson_blending, pb_solver=pb_solver, pb_num_iters=pb_num_iters,
+                                  pb_keep_original_border=pb_keep_original_border)
+    return atlas, valid_any
