@@ -113,30 +113,40 @@ __global__ void __launch_bounds__(512, 2) k_pb_jacobi(const float *__restrict__ 
     const int pc0 = blockIdx.x * kPbOutW + 4 * tx;
     const bool owner = tx >= 2 && tx < 30 && ty >= 2 && ty < 14;  // patch lies in the region's output tile
 
-    unsigned mbits = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uchar4 mm = __ldg(reinterpret_cast<const uchar4 *>(mpl + (size_t)(pr0 + i) * Wp + pc0));
-        mbits |= (mm.x ? 1u : 0u) << (4 * i) | (mm.y ? 2u : 0u) << (4 * i) | (mm.z ? 4u : 0u) << (4 * i) |
-                 (mm.w ? 8u : 0u) << (4 * i);
-    }
-    // nothing to solve in the output tile: both ping-pong planes already hold the same values there
-    if (__syncthreads_or(owner && mbits != 0) == 0) return;
-
+    // The region mask and the right-hand side were written by k_pb_setup, before the previous sweep launch: in a
+    // dependent launch they may be requested ahead of the wait, and the iterate right behind it, so that all three
+    // round trips of a block overlap (and overlap the tail of the previous launch).
+    wr_pdl_trigger();
+    uchar4 mm[4];
     float4 x[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const size_t o = chan + (size_t)(pr0 + i) * Wp + pc0;
-        x[i] = __ldg(reinterpret_cast<const float4 *>(xin + o));
-        b[i] = __ldg(reinterpret_cast<const float4 *>(bpl + o));
+        mm[i] = __ldg(reinterpret_cast<const uchar4 *>(mpl + (size_t)(pr0 + i) * Wp + pc0));
+        b[i] = __ldg(reinterpret_cast<const float4 *>(bpl + chan + (size_t)(pr0 + i) * Wp + pc0));
     }
+    wr_pdl_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(xin + chan + (size_t)(pr0 + i) * Wp + pc0);
+    unsigned mbits = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        mbits |= (mm[i].x ? 1u : 0u) << (4 * i) | (mm[i].y ? 2u : 0u) << (4 * i) | (mm[i].z ? 4u : 0u) << (4 * i) |
+                 (mm[i].w ? 8u : 0u) << (4 * i);
+    // nothing to solve in the output tile: both ping-pong planes already hold the same values there
+    if (__syncthreads_or(owner && mbits != 0) == 0) return;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // Most warps lie entirely inside or entirely outside the solve region: the per-point mask selects (three
+    // instructions each) are only executed by the warps that straddle its outline, and warps outside do nothing
+    // but keep their (zero) rows published.  The branch is warp-uniform; every warp still reaches the barrier.
+    const bool w_full = __all_sync(0xFFFFFFFFu, mbits == 0xFFFFu);
+    const bool w_empty = __all_sync(0xFFFFFFFFu, mbits == 0u);
 #pragma unroll 1
     for (int s = 0; s < sweeps; ++s) {
         const int par = s & 1;
         s_top[par][ty][tx] = x[0];
         s_bot[par][ty][tx] = x[3];
         __syncthreads();
+        if (w_empty) continue;
         const float4 up = ty > 0 ? s_bot[par][ty - 1][tx] : zero4;
         const float4 dn = ty < 15 ? s_top[par][ty + 1][tx] : zero4;
         float4 above = up;
@@ -153,11 +163,15 @@ __global__ void __launch_bounds__(512, 2) k_pb_jacobi(const float *__restrict__ 
             n.y = ((((above.y + below.y) + cur.x) + cur.z) + b[i].y) * 0.25f;
             n.z = ((((above.z + below.z) + cur.y) + cur.w) + b[i].z) * 0.25f;
             n.w = ((((above.w + below.w) + cur.z) + rt) + b[i].w) * 0.25f;
-            const unsigned mb = mbits >> (4 * i);
-            x[i].x = (mb & 1u) ? n.x : 0.0f;
-            x[i].y = (mb & 2u) ? n.y : 0.0f;
-            x[i].z = (mb & 4u) ? n.z : 0.0f;
-            x[i].w = (mb & 8u) ? n.w : 0.0f;
+            if (w_full) {
+                x[i] = n;
+            } else {
+                const unsigned mb = mbits >> (4 * i);
+                x[i].x = (mb & 1u) ? n.x : 0.0f;
+                x[i].y = (mb & 2u) ? n.y : 0.0f;
+                x[i].z = (mb & 4u) ? n.z : 0.0f;
+                x[i].w = (mb & 8u) ? n.w : 0.0f;
+            }
             above = cur;
         }
     }
@@ -365,7 +379,10 @@ extern "C" int wr_poisson_blend(wr_ctx *ctx, const float *src, const uint8_t *ma
     float *xin = P.xa, *xout = P.xb;
     for (int done = 0; done < num_iters; done += kPbHalo) {
         const int sweeps = num_iters - done < kPbHalo ? num_iters - done : kPbHalo;
-        k_pb_jacobi<<<dim3(tiles_x, tiles_y, C), 512, 0, stream>>>(xin, xout, P.b, P.m, P.Hp, P.Wp, sweeps);
+        // every launch after the first is a dependent launch of its predecessor (the first follows k_pb_setup, whose
+        // outputs it reads before its wait, so it is serialised normally)
+        wr_launch(k_pb_jacobi, dim3(tiles_x, tiles_y, C), dim3(512), stream, done > 0,
+                  (const float *)xin, xout, (const float *)P.b, (const uint8_t *)P.m, P.Hp, P.Wp, sweeps);
         WR_CHECK_LAUNCH(ctx, "k_pb_jacobi");
         float *t = xin; xin = xout; xout = t;
     }
