@@ -100,9 +100,10 @@ __device__ __forceinline__ void resolve_sample(unsigned long long *dst, float zw
 
 // Small triangle (pixel bbox <= kSmallMaxPix, snapped extent < kSmallMaxExtent): exact int32 edge
 // functions, one 64-bit atomicMin per covered sample.  DESIGN.md 3.3.
+// The rows r0, r0 + rstep, ... <= r1 are walked (rstep > 1: several lanes share one triangle, k_setup_triangles).
 __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int x2, int y2, float z0, float z1,
-                                             float z2, uint32_t id, int c0, int c1, int r0, int r1, int W, int H,
-                                             unsigned long long *depth_view)
+                                             float z2, uint32_t id, int c0, int c1, int r0, int r1, int rstep, int W,
+                                             int H, unsigned long long *depth_view)
 {
     int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);  // |extent| < 2^10: fits int32
     if (area2 < 0) {
@@ -125,7 +126,7 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
     int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
     unsigned row = (unsigned)r0 * (unsigned)W;  // pixel offsets fit 32 bits (H, W <= 8192)
 #pragma unroll 1
-    for (int r = r0; r <= r1; ++r) {
+    for (int r = r0; r <= r1; r += rstep) {
         int e0 = e0r, e1 = e1r, e2 = e2r;
 #pragma unroll 1
         for (int cc = c0; cc <= c1; ++cc) {
@@ -139,19 +140,29 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
             }
             e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
         }
-        e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
-        row += (unsigned)W;
+        e0r += 16 * rstep * dx0; e1r += 16 * rstep * dx1; e2r += 16 * rstep * dx2;
+        row += (unsigned)(rstep * W);
     }
 }
 
 // (A variant that compacted the block's live triangles through shared memory before the raster loop was
 // measured 29% SLOWER on config B -- 73.7 vs 57.3 us -- the kernel is bound by its dependent gathers,
 // not by divergence; see profiles/README.md.)
+//
+// LPT lanes per triangle.  1 for meshes of (sub-)pixel triangles.  For coarser meshes (a 50k-face object at 768^2
+// has ~6x6-pixel bounding boxes) one thread per triangle means a few hundred thousand threads that each walk up to
+// 64 samples serially -- less than two waves of the machine -- so 4 adjacent lanes share a triangle and take every
+// fourth row of its bounding box; the bound for in-thread rasterisation grows to 4 x kSmallMaxPix samples, which
+// also keeps such triangles out of the warp-per-triangle queue.  All LPT lanes read the same indices and snapped
+// vertices (same sectors), lane 0 of the group does the queue append.
+template <int LPT>
 __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0)
 {
     wr_pdl_wait();
     wr_pdl_trigger();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = gt / LPT;
+    const int sub = gt % LPT;
     const int b = blockIdx.y + view0;
     const int W = P.W, H = P.H;
     const unsigned lane = threadIdx.x & 31;
@@ -170,8 +181,10 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
             const uint32_t f_and = a.flags & c.flags & d.flags;
             if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0) {
                 if (!(f_and & WR_SV_OK)) {
-                    push = 2;
-                    entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
+                    if (sub == 0) {
+                        push = 2;
+                        entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
+                    }
                 } else {
                     x0 = a.x; y0 = a.y; x1 = c.x; y1 = c.y; x2 = d.x; y2 = d.y;
                     z0 = a.zw; z1 = c.zw; z2 = d.zw;
@@ -184,10 +197,11 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
                         const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
                         if (area2 != 0) {
                             const long long npix = (long long)(c1 - c0 + 1) * (r1 - r0 + 1);
-                            if (npix <= kSmallMaxPix && xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
-                                raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0, c1,
-                                                  r0, r1, W, H, depth_view);
-                            } else {
+                            if (npix <= kSmallMaxPix * LPT && xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
+                                if (r0 + sub <= r1)
+                                    raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0, c1,
+                                                 r0 + sub, r1, LPT, W, H, depth_view);
+                            } else if (sub == 0) {
                                 push = (npix <= kMediumMaxPix) ? 1 : 2;
                                 entry = (uint32_t)(t + P.tri_base);
                             }
@@ -612,7 +626,14 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         if (!tri_ranges) {
             wr_stage(ctx, stream, "k_setup_triangles");
             const bool pdl = !ctx->profiling && src.mvp != nullptr;  // the chain starts at k_snap_vertices_allviews
-            wr_launch(k_setup_triangles, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0);
+            // coarse mesh for this viewport (expected bounding box of a triangle above ~8 samples): 4 lanes per triangle
+#ifndef WR_SETUP_LPT4
+#define WR_SETUP_LPT4 1
+#endif
+            if (WR_SETUP_LPT4 && (long long)F * 4 <= (long long)H * W)
+                wr_launch(k_setup_triangles<4>, dim3(wr_div_up((long long)F * 4, 256), B), dim3(256), stream, pdl, P, 0);
+            else
+                wr_launch(k_setup_triangles<1>, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0);
             WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
             wr_stage(ctx, stream, "k_raster_queues");
             wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);
@@ -624,7 +645,7 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
                 if (count == 0) continue;
                 RasterParams Q = P;
                 Q.tri = tri + 3 * (size_t)start; Q.F = count; Q.tri_base = start;
-                k_setup_triangles<<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b);
+                k_setup_triangles<1><<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b);
                 WR_CHECK_LAUNCH(ctx, "k_setup_triangles(range)");
                 k_raster_queues<<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
                 WR_CHECK_LAUNCH(ctx, "k_raster_queues(range)");
