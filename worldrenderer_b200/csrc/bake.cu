@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
                                                                 float *geo_map, float *attr_map)
 {
     extern __shared__ float smem[];
+    wr_pdl_wait();   // dependent launch behind the shading kernel of the view pass (or whatever precedes it)
+    wr_pdl_trigger();
     const int pad = dilation / 2;              // max-pool halo
     const int hd = pad + 1;                    // depth halo (Sobel needs one more ring)
     const int dw = kPrepTW + 2 * hd, dh = kPrepTH + 2 * hd;
@@ -185,6 +187,8 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
 {
     constexpr bool materialise = MATERIALISE;
     extern __shared__ float s_cam[];  // [Nv,16] mvp, then [Nv] exponent
+    wr_pdl_wait();   // dependent launch behind k_view_prep
+    wr_pdl_trigger();
     for (int i = threadIdx.x; i < A.Nv * 16; i += blockDim.x) s_cam[i] = A.mvp[i];
     float *s_expo = s_cam + A.Nv * 16;
     for (int i = threadIdx.x; i < A.Nv; i += blockDim.x)
@@ -517,8 +521,8 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     const dim3 grid(wr_div_up(W, kPrepTW), wr_div_up(H, kPrepTH), B);
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_view_prep");
-    k_view_prep<<<grid, dim3(kPrepTW, kPrepBH), dilation > 0 ? smem : 0, stream>>>(
-        normal, mask, depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map);
+    wr_launch_s(k_view_prep, grid, dim3(kPrepTW, kPrepBH), dilation > 0 ? smem : 0, stream, !ctx->profiling, normal, mask,
+                depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map);
     WR_CHECK_LAUNCH(ctx, "k_view_prep");
     wr_stage(ctx, stream, "end");
     return WR_OK;
@@ -541,8 +545,8 @@ extern "C" int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void 
     const long long ntex = (long long)A.Hu * A.Wu;
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_uv_unproject");
-    if (materialise) k_uv_unproject<true><<<wr_div_up(ntex, 256), 256, smem, stream>>>(A);
-    else k_uv_unproject<false><<<wr_div_up(ntex, 256), 256, smem, stream>>>(A);
+    if (materialise) wr_launch_s(k_uv_unproject<true>, dim3(wr_div_up(ntex, 256)), dim3(256), smem, stream, !ctx->profiling, A);
+    else wr_launch_s(k_uv_unproject<false>, dim3(wr_div_up(ntex, 256)), dim3(256), smem, stream, !ctx->profiling, A);
     WR_CHECK_LAUNCH(ctx, "k_uv_unproject");
     wr_stage(ctx, stream, "end");
     return WR_OK;

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(256) k_jfa_init(const uint8_t *mask, int H, in
 __global__ void __launch_bounds__(256) k_jfa_pass(const int *__restrict__ sin, int *__restrict__ sout, int H, int W,
                                                   int step)
 {
+    wr_pdl_wait();   // every pass reads the seeds of the previous one
+    wr_pdl_trigger();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (c >= W) return;
@@ -269,6 +271,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_inpaint_fill(const T *img, const uint8_t *mask, int invert, const int *seed,
                                                       int H, int W, int C, int radius, T *out)
 {
+    wr_pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (c >= W) return;
@@ -332,13 +335,14 @@ int run_inpaint(wr_ctx *ctx, const T *img, const uint8_t *mask, int mask_is_insi
     wr_stage(ctx, stream, "k_jfa_pass");
     for (int step = top >> 1;; step >>= 1) {
         const int s = step >= 1 ? step : 1;  // the sequence ends with a second pass of step 1
-        k_jfa_pass<<<grid, 256, 0, stream>>>(sa, sb, H, W, s);
+        wr_launch(k_jfa_pass, grid, dim3(256), stream, true, (const int *)sa, sb, H, W, s);
         WR_CHECK_LAUNCH(ctx, "k_jfa_pass");
         int *t = sa; sa = sb; sb = t;
         if (step < 1) break;
     }
     wr_stage(ctx, stream, "k_inpaint_fill");
-    k_inpaint_fill<T><<<grid, 256, 0, stream>>>(img, mask, mask_is_inside, sa, H, W, C, radius, out);
+    wr_launch(k_inpaint_fill<T>, grid, dim3(256), stream, !ctx->profiling, img, mask, mask_is_inside, (const int *)sa, H, W,
+              C, radius, out);
     WR_CHECK_LAUNCH(ctx, "k_inpaint_fill");
     wr_stage(ctx, stream, "end");
     return WR_OK;

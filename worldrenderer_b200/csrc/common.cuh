@@ -148,13 +148,13 @@ __device__ __forceinline__ void wr_pdl_trigger()
 #endif
 
 template <typename... KArgs, typename... Args>
-static inline void wr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool dependent,
-                             Args... args)
+static inline void wr_launch_s(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                               bool dependent, Args... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -162,6 +162,12 @@ static inline void wr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cu
     cfg.attrs = attr;
     cfg.numAttrs = (WR_PDL && dependent) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through WR_CHECK_LAUNCH
+}
+template <typename... KArgs, typename... Args>
+static inline void wr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool dependent,
+                             Args... args)
+{
+    wr_launch_s(kernel, grid, block, 0, stream, dependent, args...);
 }
 
 #define WR_CHECK_LAUNCH(ctx, where)                                  \
