@@ -29,6 +29,7 @@
  *   wr_grid_sample                   F.grid_sample as used by uv_render_attr uv.py:200-218 (operator form)
  *   wr_uv_finalize                   hard stitch with the existing texture uv.py:452-455 (after the
  *                                    optional multi-GPU all-reduce of the accumulators)
+ *   wr_view_scores                   SmartPainter's view scoring loop smart_paint.py:118-158
  *   wr_poisson_blend                 PoissonBlendingSolver.__call__ blend.py:214-324 (Jacobi kernel blend.py:60-100)
  *   wr_uv_padding / wr_inpaint_u8    uv_padding uv.py:373-382 -> inpaint_cvc cv_ops.py:11-35 (cvcuda.inpaint)
  *
@@ -249,6 +250,16 @@ int wr_inpaint_u8(wr_ctx *ctx, const uint8_t *img, const uint8_t *mask, int H, i
  */
 int wr_uv_padding(wr_ctx *ctx, const float *attr, const uint8_t *inside_mask, int H, int W, int C, int radius,
                   float *out, void *stream);
+
+/*
+ * View scoring of SmartPainter (smart_paint.py:118-158).  attr: [B,H,W,C] f32 (channel 0 = the rendered score map),
+ * geo: [B,H,W,4] f32 from wr_render's out_geo (w = angle-of-incidence cosine, smart_paint.py:118-137).  Per view:
+ * count = #{attr < lo and aoi > aoi_min}, fsum = sum over {attr > lo and aoi > aoi_min} of max(aoi - attr - margin, 0)
+ * (the reference uses lo 1e-3, aoi_min 0.1, margin 0.3 and score = (count + fsum) / (H W)).  count: [B] i32,
+ * fsum: [B] f32 (fixed summation order, deterministic).
+ */
+int wr_view_scores(wr_ctx *ctx, const float *attr, int C, const float *geo, int B, int H, int W, float lo,
+                   float aoi_min, float margin, int32_t *count, float *fsum, void *stream);
 
 #ifdef __cplusplus
 }

@@ -221,6 +221,66 @@ def poisson_cases(mu):
     np.savez_compressed(os.path.join(OUT, "poisson.npz"), **out)
 
 
+def smart_paint_inpaint(img: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Deterministic stand-in for the inpainting network: img [1,3,H,W], mask [1,1,H,W] -> [1,3,H,W]."""
+    H, W = img.shape[-2:]
+    yy, xx = torch.meshgrid(torch.arange(H, device=img.device, dtype=torch.float32),
+                            torch.arange(W, device=img.device, dtype=torch.float32), indexing="ij")
+    pat = torch.stack([0.5 + 0.4 * torch.sin(0.05 * xx), 0.5 + 0.4 * torch.cos(0.04 * yy),
+                       0.5 + 0.4 * torch.sin(0.03 * (xx + yy))])[None]
+    return img * (1 - mask) + pat * mask
+
+
+def smart_paint_mesh():
+    """Asymmetric blob (no two candidate views score alike) with a cell atlas."""
+    v, f = synth.icosphere(5, 0.45)
+    v = v * np.array([1.0, 0.75, 0.6]) + 0.08 * np.sin(4.0 * v[:, [1, 2, 0]]) + np.array([0.03, -0.02, 0.01])
+    vt, ft = synth.cell_atlas_uv(f.shape[0])
+    return v.astype(np.float32), f.astype(np.int64), vt.astype(np.float32), ft.astype(np.int64)
+
+
+def smart_paint_case(mu):
+    """The reference's SmartPainter (smart_paint.py:37-335) on CPU, unmodified.  Test infrastructure swaps in:
+    the C oracle for nvdiffrast, the oracle's fill for cvcuda.inpaint (ref_shim), the solver backend class
+    (load_inline needs a GPU; Poisson blending is off in this loop anyway), and a recording proxy for the module's
+    `np` so that the per-round view scores can be stored."""
+    import importlib
+    blend = importlib.import_module("mvadapter.utils.mesh_utils.blend")
+    blend.PBTorchCUDAKernelBackend = blend.PBTorchNativeBackend
+    sp = importlib.import_module("mvadapter.utils.mesh_utils.smart_paint")
+    rec = {"scores": []}
+
+    class _NP:
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        def max(self, x):
+            rec["scores"].append(np.asarray(x, dtype=np.float64))
+            return np.max(x)
+
+    sp.np = _NP()
+    v, f, vt, ft = smart_paint_mesh()
+    uv = 96
+    rng = np.random.default_rng(5)
+    tex = rng.uniform(0.2, 0.8, (uv, uv, 3)).astype(np.float32)
+    m = mu.TexturedMesh(v_pos=torch.from_numpy(v), t_pos_idx=torch.from_numpy(f), v_tex=torch.from_numpy(vt),
+                        t_tex_idx=torch.from_numpy(ft), texture=torch.from_numpy(tex))
+    m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+    inpaint_mask = np.zeros((uv, uv), bool)
+    inpaint_mask[:, : uv // 2] = True      # the left half of the atlas is unpainted
+    inpaint_mask[10:30, 60:90] = True
+    painter = sp.SmartPainter("cpu", context_type="cuda")
+    torch.manual_seed(0)
+    tex_out, valid_out = painter("case", m, smart_paint_inpaint, torch.from_numpy(tex), torch.from_numpy(inpaint_mask),
+                                 min_rounds=2, max_rounds=3)
+    out = {"v_pos": v, "t_pos_idx": f.astype(np.int32), "v_tex": vt, "t_tex_idx": ft.astype(np.int32), "texture": tex,
+           "inpaint_mask": inpaint_mask, "texture_out": _np(tex_out), "valid_out": _np(valid_out),
+           "view_scores": np.stack(rec["scores"])}
+    np.savez_compressed(os.path.join(OUT, "smart_paint.npz"), **out)
+    print("smart_paint rounds", len(rec["scores"]), "best", [int(np.argmax(s)) for s in rec["scores"]],
+          "top-2 margins", [float(np.sort(s)[-1] - np.sort(s)[-2]) for s in rec["scores"]])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -232,6 +292,7 @@ def main():
     render_cases(mu)
     bake_cases(mu)
     poisson_cases(mu)
+    smart_paint_case(mu)
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
 

@@ -97,7 +97,7 @@ def _make_cvcuda() -> types.ModuleType:
     return cv
 
 
-_STUBS = ["trimesh", "imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
+_STUBS = ["cv2", "trimesh", "imageio", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
           "matplotlib.colors", "omegaconf", "pytorch_lightning", "jaxtyping", "typeguard",
           "spandrel", "gltflib", "pymeshlab", "open3d"]
 

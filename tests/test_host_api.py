@@ -160,8 +160,8 @@ def test_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             wr.NVDiffRastContextWrapper("cuda:0", "cuda")
-    with pytest.raises(NotImplementedError):
-        wr.SmartPainter()
+    with pytest.raises(RuntimeError):
+        wr.SmartPainter("cpu", "cuda")   # a caller of the path: needs a CUDA device like everything else
     with pytest.raises(NotImplementedError):
         wr.replace_mesh_texture_and_save()
 

@@ -26,6 +26,7 @@ from .render import (
     Zero123PlusPlusNormalization,
     render,
 )
+from .smart_paint import SmartPainter
 from .utils import (
     get_clip_space_position,
     image_to_tensor,
@@ -46,14 +47,6 @@ from .uv import (
     uv_render_attr,
     uv_render_geometry,
 )
-
-
-class SmartPainter:
-    """The reference's SmartPainter (smart_paint.py) drives an inpainting network around render() and
-    CameraProjection; it is a caller of the geometry path, not part of it."""
-
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("SmartPainter is outside the scope of worldrenderer_b200")
 
 
 __all__ = [

@@ -25,7 +25,7 @@ SYMBOLS = [
     "wr_status_string", "wr_ctx_last_error", "wr_version", "wr_ctx_create", "wr_ctx_destroy",
     "wr_ctx_scratch_bytes", "wr_ctx_profile", "wr_ctx_profile_read", "wr_ctx_profile_stage_name", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
     "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample", "wr_uv_reduce_finalize_p2p",
-    "wr_poisson_blend", "wr_inpaint_u8", "wr_uv_padding",
+    "wr_poisson_blend", "wr_inpaint_u8", "wr_uv_padding", "wr_view_scores",
 ]
 
 DEPTH_NONE, DEPTH_CONTROLNET, DEPTH_ZERO123PP, DEPTH_SIMPLE = 0, 1, 2, 3
@@ -131,6 +131,8 @@ def lib() -> ctypes.CDLL:
     L.wr_poisson_blend.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
     L.wr_inpaint_u8.restype = ci
     L.wr_inpaint_u8.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
+    L.wr_view_scores.restype = ci
+    L.wr_view_scores.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp, vp, vp]
     L.wr_uv_padding.restype = ci
     L.wr_uv_padding.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
     _LIB = L
