@@ -72,6 +72,12 @@ __device__ __forceinline__ V3 ld3(const float4 *p)
     V3 r; r.x = t.x; r.y = t.y; r.z = t.z;
     return r;
 }
+__device__ __forceinline__ V3 ld3s(const float *p)
+{
+    V3 r; r.x = __ldg(p); r.y = __ldg(p + 1); r.z = __ldg(p + 2);
+    return r;
+}
+
 struct TriVerts {
     V3 q0, q1, q2, n0, n1, n2;
 };
@@ -88,11 +94,18 @@ __device__ __forceinline__ TriIdx load_tri_idx(const wr_render_args &A, int id)
 
 // the normal gathers depend on the indices only: they are issued with the position gathers so that both round
 // trips overlap
+template <bool PACKED>
 __device__ __forceinline__ TriVerts gather_tri(const wr_render_args &A, const float4 *pos4, const float4 *nrm4, int id,
                                                const TriIdx &t, bool want_normal)
 {
     TriVerts v;
-    v.q0 = ld3(pos4 + t.i0); v.q1 = ld3(pos4 + t.i1); v.q2 = ld3(pos4 + t.i2);
+    constexpr bool packed = PACKED;  // the vertex pass wrote 16-byte records (wr_render decides per call)
+    if (packed) {
+        v.q0 = ld3(pos4 + t.i0); v.q1 = ld3(pos4 + t.i1); v.q2 = ld3(pos4 + t.i2);
+    } else {
+        v.q0 = ld3s(A.v_pos + 3 * (size_t)t.i0); v.q1 = ld3s(A.v_pos + 3 * (size_t)t.i1);
+        v.q2 = ld3s(A.v_pos + 3 * (size_t)t.i2);
+    }
     v.n0.x = v.n0.y = v.n0.z = 0.f;
     v.n1 = v.n0; v.n2 = v.n0;
     if (want_normal) {
@@ -102,7 +115,12 @@ __device__ __forceinline__ TriVerts gather_tri(const wr_render_args &A, const fl
             j2 = __ldg(A.tri_nrm + 3 * (size_t)id + 2);
         }
         if ((unsigned)j0 < (unsigned)A.Vn && (unsigned)j1 < (unsigned)A.Vn && (unsigned)j2 < (unsigned)A.Vn) {
-            v.n0 = ld3(nrm4 + j0); v.n1 = ld3(nrm4 + j1); v.n2 = ld3(nrm4 + j2);
+            if (packed) {
+                v.n0 = ld3(nrm4 + j0); v.n1 = ld3(nrm4 + j1); v.n2 = ld3(nrm4 + j2);
+            } else {
+                v.n0 = ld3s(A.v_nrm + 3 * (size_t)j0); v.n1 = ld3s(A.v_nrm + 3 * (size_t)j1);
+                v.n2 = ld3s(A.v_nrm + 3 * (size_t)j2);
+            }
         }
     }
     return v;
@@ -209,7 +227,7 @@ constexpr int kOutsSimpleDepth = kOutNormal | kOutDepth;                  // mas
 constexpr int kOutsBakeView = kOutGeo | kOutDepth;                        // mask + (pos, aoi_cos) + simple depth
 
 // One column strip of kShadeRows pixels per thread.  grid = (ceil(W/128), ceil(H/kShadeRows), B), 128 threads.
-template <int OUTS>
+template <int OUTS, bool PACKED>
 __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(ShadeParams P)
 {
     const wr_render_args &A = P.a;
@@ -331,7 +349,7 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
     TriVerts tv_next;
     tv_next.q0.x = tv_next.q0.y = tv_next.q0.z = 0.f;
     tv_next.q1 = tv_next.q2 = tv_next.n0 = tv_next.n1 = tv_next.n2 = tv_next.q0;
-    if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
+    if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri<PACKED>(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
 #endif
 #pragma unroll 1
     for (int k = 0; k < nrows; ++k) {
@@ -348,7 +366,7 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
 #endif
 #if WR_SHADE_PIPE >= 2
         const TriVerts tvk = tv_next;
-        if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
+        if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri<PACKED>(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
 #endif
         const bool covered = idk != 0xFFFFFFFFu;
         int id = -1;
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
             const TriIdx tik = load_tri_idx(A, id);
 #endif
 #if WR_SHADE_PIPE < 2
-            const TriVerts tvk = gather_tri(A, P.pos4, P.nrm4, id, tik, need_normal);
+            const TriVerts tvk = gather_tri<PACKED>(A, P.pos4, P.nrm4, id, tik, need_normal);
 #endif
             shade_covered(A, tvk, tik, m, id, c, r, need_normal, has_rast, has_tangent, g);
         }
@@ -544,8 +562,14 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     pack.v_nrm = want_nrm ? A.v_nrm : nullptr;
     pack.Vn = A.Vn;
     pack.offset = mask_bytes;
+    // 16-byte vertex records pay off when many pixels gather from few vertices (config A: 45.4 vs 47.4 us in
+    // k_shade); for a mesh of sub-pixel triangles writing them costs more than they save (config B: +3.3 us)
+    const bool use_pack = (long long)A.B * A.H * A.W >= 32ll * ((long long)A.V + (want_nrm ? A.Vn : 0));
+    pack.pos4 = nullptr;
+    pack.nrm4 = nullptr;
     int rc = wr_run_raster(ctx, src, A.B, A.tri, A.F, nullptr, A.H, A.W,
-                           mask_bytes + wr_vertex_pack_bytes(A.V, A.Vn, want_nrm), &res, &extra, stream, &pack);
+                           mask_bytes + (use_pack ? wr_vertex_pack_bytes(A.V, A.Vn, want_nrm) : 0), &res, &extra,
+                           stream, use_pack ? &pack : nullptr);
     if (rc != WR_OK) return rc;
 
     ShadeParams P;
@@ -567,10 +591,17 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
         // dependent launch only when the raster stages were launched (the chain's first kernel is a plain launch)
         const bool pdl = !ctx->profiling && A.F > 0 && A.V > 0;
         const dim3 block(WR_SHADE_THREADS);
-        if (plain && two_pass) wr_launch(k_shade<kOutsRenderDefault>, grid, block, stream, pdl, P);
-        else if (plain) wr_launch(k_shade<kOutsSimpleDepth>, grid, block, stream, pdl, P);
-        else if (bake) wr_launch(k_shade<kOutsBakeView>, grid, block, stream, pdl, P);
-        else wr_launch(k_shade<-1>, grid, block, stream, pdl, P);
+        if (use_pack) {
+            if (plain && two_pass) wr_launch(k_shade<kOutsRenderDefault, true>, grid, block, stream, pdl, P);
+            else if (plain) wr_launch(k_shade<kOutsSimpleDepth, true>, grid, block, stream, pdl, P);
+            else if (bake) wr_launch(k_shade<kOutsBakeView, true>, grid, block, stream, pdl, P);
+            else wr_launch(k_shade<-1, true>, grid, block, stream, pdl, P);
+        } else {
+            if (plain && two_pass) wr_launch(k_shade<kOutsRenderDefault, false>, grid, block, stream, pdl, P);
+            else if (plain) wr_launch(k_shade<kOutsSimpleDepth, false>, grid, block, stream, pdl, P);
+            else if (bake) wr_launch(k_shade<kOutsBakeView, false>, grid, block, stream, pdl, P);
+            else wr_launch(k_shade<-1, false>, grid, block, stream, pdl, P);
+        }
     }
     WR_CHECK_LAUNCH(ctx, "k_shade");
     wr_raster_consumed(ctx, &res);
