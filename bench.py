@@ -351,7 +351,7 @@ def run_ours(args):
 
     e2e_run(6)
     barrier()
-    Ke = min(K, 30)
+    Ke = min(K, 100)
     t0 = time.perf_counter()
     e2e_run(Ke)
     barrier()
