@@ -21,71 +21,68 @@ IMAGE_TYPE = Union[Image.Image, List[Image.Image], np.ndarray, torch.Tensor]
 SINGLE_IMAGE_TYPE = Union[Image.Image, np.ndarray, torch.Tensor]
 
 
+def _as_uint8(arr: np.ndarray) -> np.ndarray:
+    """float images are scaled by 255 and truncated, masks become 0 / 255, uint8 passes through."""
+    if arr.dtype in (np.float32, np.float16):
+        return (arr * 255).astype(np.uint8)
+    if arr.dtype == np.bool_:
+        return arr.astype(np.uint8) * 255
+    assert arr.dtype == np.uint8
+    return arr
+
+
 def tensor_to_image(data, batched: bool = False, format: str = "HWC"):
-    """float [0,1] / bool / uint8 array -> PIL image(s)."""
+    """float [0,1] / bool / uint8 array or tensor -> PIL image, or a list of them when `batched`
+    (utils.py:22-44).  `format="CHW"` moves the channel axis last first."""
     if isinstance(data, Image.Image):
         return data
-    if isinstance(data, torch.Tensor):
-        data = data.detach().cpu().numpy()
-    if data.dtype in (np.float32, np.float16):
-        data = (data * 255).astype(np.uint8)
-    elif data.dtype == np.bool_:
-        data = data.astype(np.uint8) * 255
-    assert data.dtype == np.uint8
-    if format == "CHW":
-        if batched and data.ndim == 4:
-            data = data.transpose((0, 2, 3, 1))
-        elif not batched and data.ndim == 3:
-            data = data.transpose((1, 2, 0))
-    if batched:
-        return [Image.fromarray(d) for d in data]
-    return Image.fromarray(data)
+    arr = _as_uint8(data.detach().cpu().numpy() if isinstance(data, torch.Tensor) else data)
+    if format == "CHW" and arr.ndim == (4 if batched else 3):
+        arr = np.moveaxis(arr, -3, -1)
+    return [Image.fromarray(a) for a in arr] if batched else Image.fromarray(arr)
 
 
 def image_to_tensor(image: IMAGE_TYPE, return_type: str = "pt", device: Optional[str] = None):
-    """PIL image(s) are scaled by 1/255; arrays and tensors are taken as they are (cast to float32)."""
+    """PIL image(s) are scaled by 1/255; arrays and tensors are taken as they are, cast to float32
+    (utils.py:47-63).  A single PIL image comes back without the batch dimension."""
     assert return_type in ["np", "pt"]
     single = isinstance(image, Image.Image)
-    if single:
-        image = [image]
-    if isinstance(image, list):
-        image = np.stack([np.array(im) for im in image], axis=0).astype(np.float32) / 255.0
-    if isinstance(image, np.ndarray) and return_type == "pt":
-        image = torch.tensor(image, device=device)
-    if isinstance(image, torch.Tensor):
-        image = image.to(dtype=torch.float32, device=device)
-    return image[0] if single else image
+    frames = [image] if single else image
+    if isinstance(frames, list):
+        frames = np.stack([np.array(f) for f in frames], axis=0).astype(np.float32) / 255.0
+    if return_type == "pt" and isinstance(frames, np.ndarray):
+        frames = torch.tensor(frames, device=device)
+    if isinstance(frames, torch.Tensor):
+        frames = frames.to(dtype=torch.float32, device=device)
+    return frames[0] if single else frames
 
 
 def largest_factor_near_sqrt(n: int) -> int:
-    root = int(math.sqrt(n))
-    if root * root == n:
-        return root
-    for i in range(root, 0, -1):
-        if n % i == 0:
-            return i
-    return 1
+    """Largest divisor of n that does not exceed sqrt(n) (1 for n < 1)."""
+    return max((d for d in range(1, math.isqrt(max(n, 1)) + 1) if n % d == 0), default=1)
 
 
 def make_image_grid(images: List[Image.Image], rows: Optional[int] = None, cols: Optional[int] = None,
                     resize: Optional[int] = None) -> Image.Image:
-    if rows is None and cols is not None:
-        assert len(images) % cols == 0
-        rows = len(images) // cols
-    elif cols is None and rows is not None:
-        assert len(images) % rows == 0
-        cols = len(images) // rows
-    elif rows is None and cols is None:
-        rows = largest_factor_near_sqrt(len(images))
-        cols = len(images) // rows
-    assert len(images) == rows * cols
-    if resize is not None:
-        images = [im.resize((resize, resize)) for im in images]
-    w, h = images[0].size
-    grid = Image.new("RGB", size=(cols * w, rows * h))
-    for i, im in enumerate(images):
-        grid.paste(im, box=(i % cols * w, i // cols * h))
-    return grid
+    """Pastes equally sized images row by row into one RGB sheet (utils.py:91-120).  A missing dimension is derived
+    from the other; with neither the sheet is made as square as the count allows."""
+    count = len(images)
+    if rows is None and cols is None:
+        rows = largest_factor_near_sqrt(count)
+    if rows is None:
+        assert count % cols == 0
+        rows = count // cols
+    elif cols is None:
+        assert count % rows == 0
+        cols = count // rows
+    assert count == rows * cols
+    tiles = images if resize is None else [t.resize((resize, resize)) for t in images]
+    tw, th = tiles[0].size
+    sheet = Image.new("RGB", size=(cols * tw, rows * th))
+    for k, tile in enumerate(tiles):
+        r, c = divmod(k, cols)
+        sheet.paste(tile, box=(c * tw, r * th))
+    return sheet
 
 
 def get_current_timestamp(fmt: str = "%Y%m%d%H%M%S") -> str:
