@@ -30,6 +30,7 @@ struct RasterParams {
     const int32_t *tri;            // [F,3] (already offset in range mode)
     int F, V, tri_base;            // tri_base: id of tri[0] (range mode)
     int W, H;
+    int ox, oy;                    // 8 - 8 W, 8 - 8 H: sub-pixel coordinate of pixel (0, 0)'s sample
     unsigned long long *depth;     // [B,H,W]
     uint32_t *queue;               // [B,Fq]
     int Fq;                        // queue stride (total triangle count)
@@ -103,9 +104,9 @@ __device__ __forceinline__ void resolve_sample(unsigned long long *dst, float zw
 // The rows r0, r0 + rstep, ... <= r1 are walked (rstep > 1: several lanes share one triangle, k_setup_triangles).
 __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int x2, int y2, float z0, float z1,
                                              float z2, uint32_t id, int c0, int c1, int r0, int r1, int rstep, int W,
-                                             int H, unsigned long long *depth_view)
+                                             int H, unsigned long long *depth_view, int area2)
 {
-    int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);  // |extent| < 2^10: fits int32
+    // area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0), computed by the caller (|extent| < 2^10: fits int32)
     if (area2 < 0) {
         int ti; float tf;
         ti = x1; x1 = x2; x2 = ti;
@@ -171,13 +172,14 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x2 = 0, y2 = 0, c0 = 0, c1 = 0, r0 = 0, r1 = 0;
     float z0 = 0.f, z1 = 0.f, z2 = 0.f;
     unsigned long long *depth_view = P.depth + (size_t)b * H * W;
-    const SnapVert *svb = P.sv + (size_t)b * P.V;
+    const unsigned vb = (unsigned)b * (unsigned)P.V;  // B * V < 2^31 (checked by the launcher): 32-bit record index
 
     if (t < P.F) {
         const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
                   i2 = __ldg(P.tri + 3 * (size_t)t + 2);
         if ((unsigned)i0 < (unsigned)P.V && (unsigned)i1 < (unsigned)P.V && (unsigned)i2 < (unsigned)P.V) {
-            const SnapVert a = load_sv32(svb, (unsigned)i0), c = load_sv32(svb, (unsigned)i1), d = load_sv32(svb, (unsigned)i2);
+            const SnapVert a = load_sv32(P.sv, vb + (unsigned)i0), c = load_sv32(P.sv, vb + (unsigned)i1),
+                           d = load_sv32(P.sv, vb + (unsigned)i2);
             const uint32_t f_and = a.flags & c.flags & d.flags;
             if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0) {
                 if (!(f_and & WR_SV_OK)) {
@@ -190,18 +192,27 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
                     z0 = a.zw; z1 = c.zw; z2 = d.zw;
                     const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
                     const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
-                    const int ox = 8 - 8 * W, oy = 8 - 8 * H;
+                    const int ox = P.ox, oy = P.oy;  // 8 - 8 W, 8 - 8 H
                     c0 = max(ceil_div16(xmin - ox), 0); c1 = min(floor_div16(xmax - ox), W - 1);
                     r0 = max(ceil_div16(ymin - oy), 0); r1 = min(floor_div16(ymax - oy), H - 1);
                     if (c0 <= c1 && r0 <= r1) {
-                        const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
-                        if (area2 != 0) {
-                            const long long npix = (long long)(c1 - c0 + 1) * (r1 - r0 + 1);
-                            if (npix <= kSmallMaxPix * LPT && xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
-                                if (r0 + sub <= r1)
-                                    raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0, c1,
-                                                 r0 + sub, r1, LPT, W, H, depth_view);
-                            } else if (sub == 0) {
+                        const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);  // <= 8192^2: fits int32
+                        if (xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
+                            // extent below 2^10 sub-pixel units: the doubled area fits int32 exactly
+                            const int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
+                            if (area2 != 0) {
+                                if (npix <= kSmallMaxPix * LPT) {
+                                    if (r0 + sub <= r1)
+                                        raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0,
+                                                     c1, r0 + sub, r1, LPT, W, H, depth_view, area2);
+                                } else if (sub == 0) {  // cannot happen for 64-px extents; kept for other thresholds
+                                    push = (npix <= kMediumMaxPix) ? 1 : 2;
+                                    entry = (uint32_t)(t + P.tri_base);
+                                }
+                            }
+                        } else if (sub == 0) {
+                            const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+                            if (area2 != 0) {
                                 push = (npix <= kMediumMaxPix) ? 1 : 2;
                                 entry = (uint32_t)(t + P.tri_base);
                             }
@@ -613,7 +624,9 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
 
     if (have_work) {
         RasterParams P;
+        if ((long long)B * V >= (1ll << 31)) return WR_ERR_UNSUPPORTED;  // 32-bit snapped-vertex record index
         P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
+        P.ox = 8 - 8 * W; P.oy = 8 - 8 * H;
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
         const int qgrid = ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
