@@ -181,20 +181,24 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
             const SnapVert a = load_sv32(P.sv, vb + (unsigned)i0), c = load_sv32(P.sv, vb + (unsigned)i1),
                            d = load_sv32(P.sv, vb + (unsigned)i2);
             const uint32_t f_and = a.flags & c.flags & d.flags;
-            if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0) {
-                if (!(f_and & WR_SV_OK)) {
-                    if (sub == 0) {
-                        push = 2;
-                        entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
-                    }
-                } else {
+            // one test for the common case: all three vertices finite and snapped, no frustum plane has all three
+            // outside; everything else (culled, or to be clipped by the queue pass) takes the cold branch
+            constexpr uint32_t kFastMask = WR_SV_FINITE | WR_SV_OK | (63u << WR_SV_OC_SHIFT);
+            if ((f_and & kFastMask) != (WR_SV_FINITE | WR_SV_OK)) {
+                if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0 && sub == 0) {
+                    push = 2;
+                    entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
+                }
+            } else {
+                {
                     x0 = a.x; y0 = a.y; x1 = c.x; y1 = c.y; x2 = d.x; y2 = d.y;
                     z0 = a.zw; z1 = c.zw; z2 = d.zw;
                     const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
                     const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
                     const int ox = P.ox, oy = P.oy;  // 8 - 8 W, 8 - 8 H
-                    c0 = max(ceil_div16(xmin - ox), 0); c1 = min(floor_div16(xmax - ox), W - 1);
-                    r0 = max(ceil_div16(ymin - oy), 0); r1 = min(floor_div16(ymax - oy), H - 1);
+                    // ceil(a / 16) == (a + 15) >> 4 with an arithmetic shift
+                    c0 = max((xmin - ox + 15) >> 4, 0); c1 = min(floor_div16(xmax - ox), W - 1);
+                    r0 = max((ymin - oy + 15) >> 4, 0); r1 = min(floor_div16(ymax - oy), H - 1);
                     if (c0 <= c1 && r0 <= r1) {
                         const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);  // <= 8192^2: fits int32
                         if (xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
