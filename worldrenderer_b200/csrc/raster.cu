@@ -632,7 +632,10 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
         P.ox = 8 - 8 * W; P.oy = 8 - 8 * H;
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
-        const int qgrid = ctx->sm_count * 2;
+        // Persistent queue pass.  A mesh of (sub-)pixel triangles rarely queues anything, and then only a few
+        // triangles (a ground plane under a dense object): a quarter of the grid is plenty for those and an empty
+        // pass drains 1.5 us sooner on config B.
+        const int qgrid = ((long long)F * 4 > (long long)H * W) ? (ctx->sm_count + 1) / 2 : ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
         if (src.mvp)
             k_snap_vertices_allviews<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
