@@ -182,6 +182,19 @@ __device__ __forceinline__ float sample1(const float *map, const Bilinear &t, in
     return acc;
 }
 
+// w^e of the exponential blend (uv.py:328-340).  pow(0, e) is 0 for e > 0 (the common case of an invalid view), and
+// the exponents in use are small integers (alpha 3 or 6 with unit view weights): those are plain products, within
+// an ulp or two of powf (the weights are compared at 1e-5); anything else goes through powf.
+__device__ __forceinline__ float blend_pow(float w, float e)
+{
+    if (w == 0.0f && e > 0.0f) return 0.0f;
+    if (e == 3.0f) return (w * w) * w;
+    if (e == 6.0f) { const float c = (w * w) * w; return c * c; }
+    if (e == 1.0f) return w;
+    if (e == 2.0f) return w * w;
+    return powf(w, e);
+}
+
 template <bool MATERIALISE>
 __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
 {
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
             }
             float wgt = geo.w * (valid ? 1.0f : 0.0f);
             // pow(0, e) is 0 for e > 0 (the common case of an invalid view): skip the call
-            wgt = (wgt == 0.0f && s_expo[v] > 0.0f) ? 0.0f : powf(wgt, s_expo[v]);
+            wgt = blend_pow(wgt, s_expo[v]);
             sw = sw + wgt;
             sr = sr + att.x * wgt; sg = sg + att.y * wgt; sb = sb + att.z * wgt;
             nvalid += valid ? 1 : 0;
