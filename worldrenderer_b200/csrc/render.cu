@@ -5,12 +5,19 @@
 // nvdiffrast-layout rast tensor and the textured attribute map -- everything render() returns, written
 // once.  Operation order of every expression: DESIGN.md 3.4-3.6 / 4 (same as oracle/).
 //
-//   k_shade           one pixel per thread, no shared memory and no block barrier: a warp whose 32 pixels
-//                     are background (78% of the warps of config B) is one 8-byte load and its stores.
+//   k_shade           one 4-row column strip per thread, 128 threads, 64 registers, no shared memory and no
+//                     block barrier.  The four triangle ids of a strip (low words of the packed entries) are
+//                     requested first; a warp whose strips are all background (78% of the warps of config B)
+//                     writes its constant rows with 16-byte stores; covered pixels gather indices, then the
+//                     vertices (16-byte records from the vertex pass for coarse meshes, PACKED), and derive
+//                     everything render() returns.  The per-view depth range is reduced per warp and
+//                     published with an atomic only when it improves an L1-cached read of the current range.
 //                     Measured alternatives that LOST on config B (profiles/README.md): transposing the
-//                     3-channel stores through shared memory (+7%), forcing 6 blocks/SM (+3%, spills),
-//                     four pixels per thread with 16-byte loads/stores (+22%: the covered path serialises).
-//   k_depth_finalize  second depth pass for normalisers that need the per-view min / max.
+//                     3-channel stores through shared memory (+7%), four pixels per thread with 16-byte
+//                     accesses (+22%), a shared-memory prologue with a block barrier (+5%), prefetching the
+//                     gathers of the next row (+17%), 48 registers / 10 blocks per SM (+4%, spills).
+//   k_depth_finalize  second depth pass for normalisers that need the per-view min / max (covered pixels only:
+//                     the constant background value is written by k_shade).
 //
 // The shading kernel resets every packed entry it consumes to WR_EMPTY_PIXEL, which leaves the
 // buffer clean for the next call (no clear pass).
@@ -208,12 +215,6 @@ __device__ __forceinline__ void shade_covered(const wr_render_args &A, const Tri
 #ifndef WR_SHADE_MINB
 #define WR_SHADE_MINB 8   // 64 registers: measured 47.3 us vs 49.6 us unconstrained on config B
 #endif
-#ifndef WR_SHADE_PIPE
-#define WR_SHADE_PIPE 0
-#endif
-#ifndef WR_SHADE_NOBAR
-#define WR_SHADE_NOBAR 1   // measured 45.1 us vs 47.4 us with the shared-memory prologue + barrier
-#endif
 #ifndef WR_SHADE_THREADS
 #define WR_SHADE_THREADS 128
 #endif
@@ -261,7 +262,6 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
 #pragma unroll
     for (int k = 0; k < kShadeRows; ++k) idw[k] = (k < nrows) ? pk32[2 * (o0 + (size_t)k * W)] : 0xFFFFFFFFu;
 
-#if WR_SHADE_NOBAR
     // No shared memory and no block barrier: the view's matrices are read where they are used (one address for
     // the whole warp, served by L1), and the depth range is published per warp behind a cached read of the
     // current range -- a stale value only costs a redundant atomic, the range grows monotonically.
@@ -271,26 +271,6 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
         const float *m2 = A.w2c + 16 * b + 8;
         wz0 = __ldg(m2); wz1 = __ldg(m2 + 1); wz2 = __ldg(m2 + 2); wz3 = __ldg(m2 + 3);
     }
-#else
-    // Block prologue: the view's matrices go to shared memory (read back as broadcasts in the covered path, which
-    // keeps 20 registers free), and the per-block depth range is initialised.  This is the only block barrier;
-    // afterwards warps retire independently and the last one to finish publishes the block's range -- and only
-    // if it improves on the range seen at entry (after the first wave almost none does).
-    __shared__ float s_m[16];
-    __shared__ float s_wz[4];
-    __shared__ uint32_t s_lo, s_hi, s_done, s_seen_lo, s_seen_hi;
-    if (threadIdx.x < 16) s_m[threadIdx.x] = __ldg(A.mvp + 16 * b + threadIdx.x);
-    if (has_depth && threadIdx.x >= 32 && threadIdx.x < 36) s_wz[threadIdx.x - 32] = __ldg(A.w2c + 16 * b + 8 + (threadIdx.x - 32));
-    if (two_pass && threadIdx.x == 64) {
-        s_lo = 0u; s_hi = 0u; s_done = 0u;
-        s_seen_lo = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b);
-        s_seen_hi = *reinterpret_cast<volatile uint32_t *>(P.range + 4 * b + 1);
-    }
-    __syncthreads();
-    const float *m = s_m;
-    float wz0 = 0.f, wz1 = 0.f, wz2 = 0.f, wz3 = 0.f;
-    if (has_depth) { wz0 = s_wz[0]; wz1 = s_wz[1]; wz2 = s_wz[2]; wz3 = s_wz[3]; }
-#endif
     const float nbx = A.normal_bg[0], nby = A.normal_bg[1], nbz = A.normal_bg[2];
     float rot[9];
     if (has_geo) {
@@ -334,23 +314,10 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
         }
     }
 
-    // Covered pixels need two dependent gathers (id -> vertex indices -> vertex records).  Walking the strip row by
-    // row would serialise 2 x rows round trips per thread, so (WR_SHADE_PIPE >= 1) the index loads of all rows are
-    // issued together, and (>= 2) the vertex records of row k+1 are requested before row k is shaded.
-#if WR_SHADE_PIPE >= 1
-    TriIdx tix[kShadeRows];
-#pragma unroll
-    for (int k = 0; k < kShadeRows; ++k) {
-        tix[k].i0 = tix[k].i1 = tix[k].i2 = 0;
-        if (idw[k] != 0xFFFFFFFFu) tix[k] = load_tri_idx(A, (int)idw[k]);
-    }
-#endif
-#if WR_SHADE_PIPE >= 2
-    TriVerts tv_next;
-    tv_next.q0.x = tv_next.q0.y = tv_next.q0.z = 0.f;
-    tv_next.q1 = tv_next.q2 = tv_next.n0 = tv_next.n1 = tv_next.n2 = tv_next.q0;
-    if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri<PACKED>(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
-#endif
+    // Covered pixels need two dependent gathers (id -> vertex indices -> vertex records), row after row.  Issuing
+    // the index loads of all rows together, or requesting the records of row k+1 before row k is shaded, was
+    // measured: 45.7 / 52.9 us against 45.1 us for this plain loop (profiles/README.md) -- other warps hide the
+    // round trips better than the extra registers do.
 #pragma unroll 1
     for (int k = 0; k < nrows; ++k) {
         const int r = r0 + k;
@@ -359,15 +326,6 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
 #pragma unroll
         for (int j = 0; j + 1 < kShadeRows; ++j) idw[j] = idw[j + 1];  // register rotation: no indexed local array
         idw[kShadeRows - 1] = 0xFFFFFFFFu;
-#if WR_SHADE_PIPE >= 1
-        const TriIdx tik = tix[0];
-#pragma unroll
-        for (int j = 0; j + 1 < kShadeRows; ++j) tix[j] = tix[j + 1];
-#endif
-#if WR_SHADE_PIPE >= 2
-        const TriVerts tvk = tv_next;
-        if (idw[0] != 0xFFFFFFFFu) tv_next = gather_tri<PACKED>(A, P.pos4, P.nrm4, (int)idw[0], tix[0], need_normal);
-#endif
         const bool covered = idk != 0xFFFFFFFFu;
         int id = -1;
         PixelGeo g;
@@ -378,12 +336,8 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
         if (covered) {
             P.packed[o] = WR_EMPTY_PIXEL;  // self-cleaning
             id = (int)idk;
-#if WR_SHADE_PIPE == 0
             const TriIdx tik = load_tri_idx(A, id);
-#endif
-#if WR_SHADE_PIPE < 2
             const TriVerts tvk = gather_tri<PACKED>(A, P.pos4, P.nrm4, id, tik, need_normal);
-#endif
             shade_covered(A, tvk, tik, m, id, c, r, need_normal, has_rast, has_tangent, g);
         }
         if (has_mask) P.mask[o] = covered ? 1 : 0;
@@ -448,27 +402,11 @@ publish:
         // last warp of the block issues at most one global atomic pair
         lo = warp_min(lo);
         hi = warp_max(hi);
-#if WR_SHADE_NOBAR
         if ((threadIdx.x & 31) == 0) {
             const uint32_t seen_lo = __ldg(P.range + 4 * b), seen_hi = __ldg(P.range + 4 * b + 1);
             if (lo < INFINITY && ~wr_float_ordered(lo) > seen_lo) atomicMax(P.range + 4 * b, ~wr_float_ordered(lo));
             if (hi > -INFINITY && wr_float_ordered(hi) > seen_hi) atomicMax(P.range + 4 * b + 1, wr_float_ordered(hi));
         }
-#else
-        if ((threadIdx.x & 31) == 0) {
-            if (lo < INFINITY) atomicMax(&s_lo, ~wr_float_ordered(lo));
-            if (hi > -INFINITY) atomicMax(&s_hi, wr_float_ordered(hi));
-            __threadfence_block();
-            const uint32_t nwarps = (blockDim.x + 31) >> 5;
-            if (atomicAdd(&s_done, 1u) == nwarps - 1) {
-                __threadfence_block();
-                const uint32_t klo = *reinterpret_cast<volatile uint32_t *>(&s_lo);
-                const uint32_t khi = *reinterpret_cast<volatile uint32_t *>(&s_hi);
-                if (klo > s_seen_lo) atomicMax(P.range + 4 * b, klo);
-                if (khi > s_seen_hi) atomicMax(P.range + 4 * b + 1, khi);
-            }
-        }
-#endif
     }
 }
 
