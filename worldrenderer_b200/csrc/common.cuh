@@ -22,7 +22,8 @@
 #define WR_QUEUE_SLOW 0x80000000u  // queue entry flag: triangle needs geometric clipping
 
 struct __align__(16) SnapVert {
-    int x, y;        // 1/16 pixel units, origin at the viewport centre
+    int x, y;        // 1/16 pixel units relative to the sample of pixel (0, 0): round(ndc * 8 * size) + 8 * size - 8,
+                     // so that pixel (c, r) samples (16 c, 16 r) and its column is x >> 4 without an offset
     float zw;        // z/w
     uint32_t flags;
 };

@@ -30,7 +30,6 @@ struct RasterParams {
     const int32_t *tri;            // [F,3] (already offset in range mode)
     int F, V, tri_base;            // tri_base: id of tri[0] (range mode)
     int W, H;
-    int ox, oy;                    // 8 - 8 W, 8 - 8 H: sub-pixel coordinate of pixel (0, 0)'s sample
     unsigned long long *depth;     // [B,H,W]
     uint32_t *queue;               // [B,Fq]
     int Fq;                        // queue stride (total triangle count)
@@ -69,8 +68,8 @@ __global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, in
         const float fx = (p.x * (float)(8 * W)) * rw;
         const float fy = (p.y * (float)(8 * H)) * rw;
         if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
-            s.x = __float2int_rn(fx);
-            s.y = __float2int_rn(fy);
+            s.x = __float2int_rn(fx) + (8 * W - 8);   // relative to the sample of pixel (0, 0): see SnapVert
+            s.y = __float2int_rn(fy) + (8 * H - 8);
             s.zw = p.z * rw;
             flags |= WR_SV_OK;
         }
@@ -121,7 +120,7 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
     const int bias1 = top_left(dx1, dy1) ? 0 : 1;
     const int bias2 = top_left(dx2, dy2) ? 0 : 1;
     const float inv_area = 1.0f / __int2float_rn(area2);
-    const int px0 = 16 * c0 + (8 - 8 * W), py0 = 16 * r0 + (8 - 8 * H);
+    const int px0 = 16 * c0, py0 = 16 * r0;  // snapped coordinates are relative to the sample of pixel (0, 0)
     int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
     int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
     int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
@@ -195,10 +194,9 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
                     z0 = a.zw; z1 = c.zw; z2 = d.zw;
                     const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
                     const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
-                    const int ox = P.ox, oy = P.oy;  // 8 - 8 W, 8 - 8 H
-                    // ceil(a / 16) == (a + 15) >> 4 with an arithmetic shift
-                    c0 = max((xmin - ox + 15) >> 4, 0); c1 = min(floor_div16(xmax - ox), W - 1);
-                    r0 = max((ymin - oy + 15) >> 4, 0); r1 = min(floor_div16(ymax - oy), H - 1);
+                    // pixel (c, r) samples (16 c, 16 r); ceil(a / 16) == (a + 15) >> 4 with an arithmetic shift
+                    c0 = max((xmin + 15) >> 4, 0); c1 = min(xmax >> 4, W - 1);
+                    r0 = max((ymin + 15) >> 4, 0); r1 = min(ymax >> 4, H - 1);
                     if (c0 <= c1 && r0 <= r1) {
                         const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);  // <= 8192^2: fits int32
                         if (xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
@@ -301,8 +299,8 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
             const float fx = unit_w ? (c.x * (float)(8 * W)) : (c.x * (float)(8 * W)) * rw;
             const float fy = unit_w ? (c.y * (float)(8 * H)) : (c.y * (float)(8 * H)) * rw;
             if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
-                s.x = __float2int_rn(fx);
-                s.y = __float2int_rn(fy);
+                s.x = __float2int_rn(fx) + (8 * W - 8);
+                s.y = __float2int_rn(fy) + (8 * H - 8);
                 s.zw = c.z * rw;
                 flags |= WR_SV_OK;
             }
@@ -334,9 +332,8 @@ __device__ void warp_raster_impl(int x0, int y0, int x1, int y1, int x2, int y2,
     }
     const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
     const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
-    const int ox = 8 - 8 * W, oy = 8 - 8 * H;
-    const int c0 = max(ceil_div16(xmin - ox), 0), c1 = min(floor_div16(xmax - ox), W - 1);
-    const int r0 = max(ceil_div16(ymin - oy), 0), r1 = min(floor_div16(ymax - oy), H - 1);
+    const int c0 = max(ceil_div16(xmin), 0), c1 = min(floor_div16(xmax), W - 1);
+    const int r0 = max(ceil_div16(ymin), 0), r1 = min(floor_div16(ymax), H - 1);
     if (c0 > c1 || r0 > r1) return;
     const int dx0 = x2 - x1, dy0 = y2 - y1;
     const int dx1 = x0 - x2, dy1 = y0 - y2;
@@ -355,9 +352,9 @@ __device__ void warp_raster_impl(int x0, int y0, int x1, int y1, int x2, int y2,
         for (int fy = rl & ~3; fy <= rh; fy += 4) {
             const int rr = fy + ly;
             const bool row_in = rr >= rl && rr <= rh;
-            const int py = 16 * rr + oy;
+            const int py = 16 * rr;
             int cc = (cl & ~7) + lx;
-            const int px = 16 * cc + ox;
+            const int px = 16 * cc;
             E e0 = (E)dx0 * (py - y1) - (E)dy0 * (px - x1);
             E e1 = (E)dx1 * (py - y2) - (E)dy1 * (px - x2);
             E e2 = (E)dx2 * (py - y0) - (E)dy2 * (px - x0);
@@ -390,7 +387,7 @@ __device__ void warp_raster_impl(int x0, int y0, int x1, int y1, int x2, int y2,
             const int cl = max(c0, bx * kB), ch = min(c1, bx * kB + kB - 1);
             const int rl = max(r0, by * kB), rh = min(r1, by * kB + kB - 1);
             // conservative reject: evaluate every edge at the block corner where it is largest
-            const int pxl = 16 * cl + ox, pxh = 16 * ch + ox, pyl = 16 * rl + oy, pyh = 16 * rh + oy;
+            const int pxl = 16 * cl, pxh = 16 * ch, pyl = 16 * rl, pyh = 16 * rh;
             const E m0 = (E)dx0 * ((dx0 >= 0 ? pyh : pyl) - y1) - (E)dy0 * ((dy0 >= 0 ? pxl : pxh) - x1);
             const E m1 = (E)dx1 * ((dx1 >= 0 ? pyh : pyl) - y2) - (E)dy1 * ((dy1 >= 0 ? pxl : pxh) - x2);
             const E m2 = (E)dx2 * ((dx2 >= 0 ? pyh : pyl) - y0) - (E)dy2 * ((dy2 >= 0 ? pxl : pxh) - x0);
@@ -506,8 +503,8 @@ __device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc
                         const float fx = (p.x * (float)(8 * P.W)) * rw;
                         const float fy = (p.y * (float)(8 * P.H)) * rw;
                         if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
-                            S.X[i] = __float2int_rn(fx);
-                            S.Y[i] = __float2int_rn(fy);
+                            S.X[i] = __float2int_rn(fx) + (8 * P.W - 8);
+                            S.Y[i] = __float2int_rn(fy) + (8 * P.H - 8);
                             S.zw[i] = p.z * rw;
                             ok = true;
                         }
@@ -630,7 +627,6 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         RasterParams P;
         if ((long long)B * V >= (1ll << 31)) return WR_ERR_UNSUPPORTED;  // 32-bit snapped-vertex record index
         P.sv = sv; P.tri = tri; P.F = F; P.V = V; P.tri_base = 0; P.W = W; P.H = H;
-        P.ox = 8 - 8 * W; P.oy = 8 - 8 * H;
         P.depth = depth; P.queue = queue; P.Fq = F; P.counters = stats;
         // Persistent queue pass.  A mesh of (sub-)pixel triangles rarely queues anything, and then only a few
         // triangles (a ground plane under a dense object): a quarter of the grid is plenty for those and an empty
