@@ -12,10 +12,13 @@ data-path collective -- so scaling is weak and `value` = N * 6 * K / (max over r
 JSON keys beyond the base contract:
   roofline      dominant kernel: algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json
   pipeline      whole render step against the same peak (12F + 24V + 33HW bytes per view)
-  stages        per-kernel ms (CUDA events recorded by the library on its launch stream)
+  stages        per-kernel ms (CUDA events recorded by the library on its launch stream; recording them
+                turns the dependent launches off, so the stages sum to more than ms_per_step)
   cpu_baseline  the oracle port of the reference's render path timed on this box's host cores
   e2e           same metric through the public API with host buffers (H2D of the mesh, D2H of the maps)
-  bake          ms per UV bake, config C (6 x 768^2 images -> 1024^2 atlas), device resident
+  bake          ms per UV bake, config C (6 x 768^2 images -> 1024^2 atlas), device resident: the
+                CameraProjection call of SURVEY 8d, the unprojection kernel alone, and the same call with the
+                reference's default tail (seam padding; padding + 1000 Poisson sweeps)
 
 `--impl reference` times the reference's render path on the host cores.  The reference has no CPU
 implementation of its own (its rasterizer is the GPU-only nvdiffrast), so this arm is the oracle

@@ -70,6 +70,21 @@ def test_icosphere_canonical_rig(wr_ctx, strategy, spec):
     _compare(out, _oracle(mesh, cam, 160, 160, spec))
 
 
+@pytest.mark.parametrize("H,W", [(30, 34), (33, 31), (7, 5), (64, 36), (1, 16), (50, 50)])
+@pytest.mark.parametrize("strategy,spec", [STRATEGIES[0], STRATEGIES[2], STRATEGIES[5]])
+def test_viewport_shapes_take_every_store_and_finalize_path(wr_ctx, H, W, strategy, spec):
+    """H*W a multiple of 16 / of 4 only / of neither, W a multiple of 4 or not: the second depth pass has a
+    16-pixel, a 4-pixel and a scalar form, and the background rows of the shading kernel a 16-byte-store form."""
+    v, f = cases.icosphere_mesh(6)
+    mesh = make_mesh(v, f, wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    out = wr.render(wr_ctx, mesh, cam, H, W, render_attr=False, depth_normalization_strategy=strategy)
+    ref = _oracle(mesh, cam, H, W, spec)
+    _compare(out, ref)
+    for k in ("pos", "normal", "depth"):
+        np.testing.assert_array_equal(getattr(out, k).cpu().numpy(), ref[k], err_msg=k)
+
+
 def test_tri_ids_and_rast_fused(wr_ctx):
     v, f = cases.terrain_mesh(128, 64)
     mesh = make_mesh(v, f, wr_ctx.device)
