@@ -26,7 +26,7 @@ from . import _native
 from .camera import Camera, get_camera
 from .mesh import TexturedMesh, mesh_use_texture
 from .projection import CameraProjection
-from .render import NVDiffRastContextWrapper, render, render_geometry_raw
+from .render import DepthControlNetNormalization, NVDiffRastContextWrapper, render, render_geometry_raw
 from .utils import make_image_grid, tensor_to_image
 from .uv import uv_padding
 
@@ -100,7 +100,7 @@ class SmartPainter:
         raw = render_geometry_raw(self.ctx, mesh, cam, size, size, want_pos=False, want_depth=True, want_normal=False,
                                   want_attr=True, want_geo=True, attr_background=1.0, texture_override=tex,
                                   texture_filter_mode="nearest",
-                                  depth_normalization_strategy=_default_depth_strategy())
+                                  depth_normalization_strategy=DepthControlNetNormalization())  # render()'s default (:248)
         score = raw["attr"][0, :, :, 0]
         aoi = raw["geo"][0, :, :, 3]
         mask = (score < _ATTR_EPS) | (aoi - score > _MARGIN)                 # :245-247
@@ -159,7 +159,3 @@ class SmartPainter:
             texture = uv_padding(texture, painted, 3)
         return texture, painted
 
-
-def _default_depth_strategy():
-    from .render import DepthControlNetNormalization
-    return DepthControlNetNormalization()   # render()'s default, which the reference's depth[0] carries (:248)
