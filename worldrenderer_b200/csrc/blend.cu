@@ -23,6 +23,10 @@ constexpr int kPbHalo = 8;                      // sweeps per launch = halo widt
 constexpr int kPbRegW = 128, kPbRegH = 64;      // region held by one 512-thread block
 constexpr int kPbOutW = kPbRegW - 2 * kPbHalo;  // 112
 constexpr int kPbOutH = kPbRegH - 2 * kPbHalo;  // 48
+#ifndef WR_PB_ROWS
+#define WR_PB_ROWS 8
+#endif
+constexpr int kPbRows = WR_PB_ROWS;             // region rows per thread (4 columns wide)
 
 struct PbPlanes {
     int H, W, C;
@@ -100,60 +104,67 @@ __global__ void __launch_bounds__(256) k_pb_setup(const float *src, const uint8_
 
 // `sweeps` (<= kPbHalo) Jacobi sweeps of one 128x64 region of one channel plane; the inner 112x48 points are
 // exact after them (every sweep invalidates one more ring of the region) and are written to xout.
-__global__ void __launch_bounds__(512, 2) k_pb_jacobi(const float *__restrict__ xin, float *__restrict__ xout,
-                                                      const float *__restrict__ bpl, const uint8_t *__restrict__ mpl,
-                                                      int Hp, int Wp, int sweeps)
+// R = rows of the region per thread (4 columns wide): 4 -> 512 threads, 8 -> 256 threads with twice the
+// independent work per thread and half the barriers, shuffles and shared-memory rows per point.
+template <int R>
+__global__ void __launch_bounds__(32 * (kPbRegH / R), 2) k_pb_jacobi(const float *__restrict__ xin, float *__restrict__ xout,
+                                                                     const float *__restrict__ bpl,
+                                                                     const uint8_t *__restrict__ mpl, int Hp, int Wp,
+                                                                     int sweeps)
 {
-    __shared__ float4 s_top[2][16][32];  // first row of every warp's 4-row band, per parity
-    __shared__ float4 s_bot[2][16][32];  // last row
+    constexpr int kBands = kPbRegH / R;           // warps per block
+    __shared__ float4 s_top[2][kBands][32];       // first row of every warp's R-row band, per parity
+    __shared__ float4 s_bot[2][kBands][32];       // last row
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const size_t plane = (size_t)Hp * Wp;
     const size_t chan = (size_t)blockIdx.z * plane;
-    const int pr0 = blockIdx.y * kPbOutH + 4 * ty;  // padded-plane coordinates of this thread's 4x4 patch
+    const int pr0 = blockIdx.y * kPbOutH + R * ty;  // padded-plane coordinates of this thread's R x 4 patch
     const int pc0 = blockIdx.x * kPbOutW + 4 * tx;
-    const bool owner = tx >= 2 && tx < 30 && ty >= 2 && ty < 14;  // patch lies in the region's output tile
+    // patch lies in the region's output tile (the halo is a whole number of patches in both directions)
+    const bool owner = tx >= 2 && tx < 30 && ty >= kPbHalo / R && ty < (kPbRegH - kPbHalo) / R;
+    static_assert(kPbHalo % R == 0 && kPbRegH % R == 0 && R * 4 <= 32, "patch rows must tile the halo");
 
     // The region mask and the right-hand side were written by k_pb_setup, before the previous sweep launch: in a
     // dependent launch they may be requested ahead of the wait, and the iterate right behind it, so that all three
     // round trips of a block overlap (and overlap the tail of the previous launch).
     wr_pdl_trigger();
-    uchar4 mm[4];
-    float4 x[4], b[4];
+    uchar4 mm[R];
+    float4 x[R], b[R];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
         mm[i] = __ldg(reinterpret_cast<const uchar4 *>(mpl + (size_t)(pr0 + i) * Wp + pc0));
         b[i] = __ldg(reinterpret_cast<const float4 *>(bpl + chan + (size_t)(pr0 + i) * Wp + pc0));
     }
     wr_pdl_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4 *>(xin + chan + (size_t)(pr0 + i) * Wp + pc0);
+    for (int i = 0; i < R; ++i) x[i] = *reinterpret_cast<const float4 *>(xin + chan + (size_t)(pr0 + i) * Wp + pc0);
     unsigned mbits = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        mbits |= (mm[i].x ? 1u : 0u) << (4 * i) | (mm[i].y ? 2u : 0u) << (4 * i) | (mm[i].z ? 4u : 0u) << (4 * i) |
-                 (mm[i].w ? 8u : 0u) << (4 * i);
+    for (int i = 0; i < R; ++i)
+        mbits |= ((mm[i].x ? 1u : 0u) | (mm[i].y ? 2u : 0u) | (mm[i].z ? 4u : 0u) | (mm[i].w ? 8u : 0u)) << (4 * i);
     // nothing to solve in the output tile: both ping-pong planes already hold the same values there
     if (__syncthreads_or(owner && mbits != 0) == 0) return;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     // Most warps lie entirely inside or entirely outside the solve region: the per-point mask selects (three
     // instructions each) are only executed by the warps that straddle its outline, and warps outside do nothing
     // but keep their (zero) rows published.  The branch is warp-uniform; every warp still reaches the barrier.
-    const bool w_full = __all_sync(0xFFFFFFFFu, mbits == 0xFFFFu);
+    constexpr unsigned kAll = R * 4 == 32 ? 0xFFFFFFFFu : ((1u << (R * 4)) - 1u);
+    const bool w_full = __all_sync(0xFFFFFFFFu, mbits == kAll);
     const bool w_empty = __all_sync(0xFFFFFFFFu, mbits == 0u);
 #pragma unroll 1
     for (int s = 0; s < sweeps; ++s) {
         const int par = s & 1;
         s_top[par][ty][tx] = x[0];
-        s_bot[par][ty][tx] = x[3];
+        s_bot[par][ty][tx] = x[R - 1];
         __syncthreads();
         if (w_empty) continue;
         const float4 up = ty > 0 ? s_bot[par][ty - 1][tx] : zero4;
-        const float4 dn = ty < 15 ? s_top[par][ty + 1][tx] : zero4;
+        const float4 dn = ty < kBands - 1 ? s_top[par][ty + 1][tx] : zero4;
         float4 above = up;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < R; ++i) {
             const float4 cur = x[i];
-            const float4 below = (i < 3) ? x[i + 1] : dn;
+            const float4 below = (i < R - 1) ? x[i + 1] : dn;
             float lf = __shfl_up_sync(0xFFFFFFFFu, cur.w, 1);
             float rt = __shfl_down_sync(0xFFFFFFFFu, cur.x, 1);
             if (tx == 0) lf = 0.0f;
@@ -177,7 +188,7 @@ __global__ void __launch_bounds__(512, 2) k_pb_jacobi(const float *__restrict__ 
     }
     if (owner) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < R; ++i)
             *reinterpret_cast<float4 *>(xout + chan + (size_t)(pr0 + i) * Wp + pc0) = x[i];
     }
 }
@@ -385,7 +396,7 @@ extern "C" int wr_poisson_blend(wr_ctx *ctx, const float *src, const uint8_t *ma
         const int sweeps = num_iters - done < kPbHalo ? num_iters - done : kPbHalo;
         // every launch after the first is a dependent launch of its predecessor (the first follows k_pb_setup, whose
         // outputs it reads before its wait, so it is serialised normally)
-        wr_launch(k_pb_jacobi, dim3(tiles_x, tiles_y, C), dim3(512), stream, done > 0,
+        wr_launch(k_pb_jacobi<kPbRows>, dim3(tiles_x, tiles_y, C), dim3(32 * (kPbRegH / kPbRows)), stream, done > 0,
                   (const float *)xin, xout, (const float *)P.b, (const uint8_t *)P.m, P.Hp, P.Wp, sweeps);
         WR_CHECK_LAUNCH(ctx, "k_pb_jacobi");
         float *t = xin; xin = xout; xout = t;
