@@ -4,7 +4,7 @@
 //                      lists (A [N,4] int64) and launches one Jacobi kernel per sweep with a
 //                      cudaDeviceSynchronize after each (blend.py:60-100).  Here the solve region stays a 2-D
 //                      image: planar, zero-padded scratch planes, and a temporally blocked stencil kernel
-//                      that runs 8 sweeps per launch out of registers (4x4 points per thread; up / down
+//                      that runs 8 sweeps per launch out of registers (4x8 points per thread; up / down
 //                      neighbours through two shared-memory rows per warp, left / right by warp shuffle).
 //   wr_inpaint         uv_padding -> inpaint_cvc uv.py:373-382, cv_ops.py:11-35: quantisation contract of the
 //                      reference, fill by jump flooding + inverse-square-distance average (the cvcuda operator
@@ -20,7 +20,7 @@ namespace {
 // Poisson blending
 // ------------------------------------------------------------------------------------------------
 constexpr int kPbHalo = 8;                      // sweeps per launch = halo width of a region
-constexpr int kPbRegW = 128, kPbRegH = 64;      // region held by one 512-thread block
+constexpr int kPbRegW = 128, kPbRegH = 64;      // region held by one block (32 x 64 / kPbRows threads)
 constexpr int kPbOutW = kPbRegW - 2 * kPbHalo;  // 112
 constexpr int kPbOutH = kPbRegH - 2 * kPbHalo;  // 48
 #ifndef WR_PB_ROWS
