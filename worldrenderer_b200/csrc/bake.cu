@@ -40,33 +40,38 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
     const int x0 = blockIdx.x * kPrepTW, y0 = blockIdx.y * kPrepTH;
     if (dilation > 0) {
         const float *dv = depth + (size_t)b * H * W;
-        // 2-D strided loops (no integer division): rows by threadIdx.y, columns by threadIdx.x
-        for (int ry = threadIdx.y; ry < dh; ry += kPrepBH) {
-            const int yy = y0 - hd + ry;
-            const bool yin = yy >= 0 && yy < H;
-            for (int rx = threadIdx.x; rx < dw; rx += kPrepTW) {
-                const int xx = x0 - hd + rx;
-                s_d[ry * dw + rx] = (yin && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
-            }
+        // The tiles are 32 + 2 * halo columns wide.  Rows go by threadIdx.y and the first 32 columns by threadIdx.x
+        // (no integer division); the few halo columns beyond 32 are walked as one flat list by the whole block, so
+        // that no pass runs with only a handful of lanes.
+        const int tid = threadIdx.y * kPrepTW + threadIdx.x;
+        auto load_depth = [&](int ry, int rx) {
+            const int yy = y0 - hd + ry, xx = x0 - hd + rx;
+            s_d[ry * dw + rx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
+        };
+        for (int ry = threadIdx.y; ry < dh; ry += kPrepBH) load_depth(ry, threadIdx.x);
+        {
+            const int extra = dw - kPrepTW;
+            for (int e = tid; e < extra * dh; e += kPrepTW * kPrepBH) load_depth(e / extra, kPrepTW + e % extra);
         }
         __syncthreads();
-        for (int gy_ = threadIdx.y; gy_ < gh; gy_ += kPrepBH) {
-            const int yy = y0 - pad + gy_;
-            const bool yin = yy >= 0 && yy < H;
-            for (int gx_ = threadIdx.x; gx_ < gw; gx_ += kPrepTW) {
-                const int xx = x0 - pad + gx_;
-                float g = -INFINITY;
-                if (yin && xx >= 0 && xx < W) {
-                    const float *c = s_d + (gy_ + 1) * dw + (gx_ + 1);  // centre of the 3x3 window in the depth tile
-                    const float s00 = c[-dw - 1], s01 = c[-dw], s02 = c[-dw + 1];
-                    const float s10 = c[-1], s12 = c[1];
-                    const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
-                    const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
-                    const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
-                    g = sqrtf(gx * gx + gy * gy);
-                }
-                s_g[gy_ * gw + gx_] = g;
+        auto sobel = [&](int gy_, int gx_) {
+            const int yy = y0 - pad + gy_, xx = x0 - pad + gx_;
+            float g = -INFINITY;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const float *c = s_d + (gy_ + 1) * dw + (gx_ + 1);  // centre of the 3x3 window in the depth tile
+                const float s00 = c[-dw - 1], s01 = c[-dw], s02 = c[-dw + 1];
+                const float s10 = c[-1], s12 = c[1];
+                const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
+                const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
+                const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
+                g = sqrtf(gx * gx + gy * gy);
             }
+            s_g[gy_ * gw + gx_] = g;
+        };
+        for (int gy_ = threadIdx.y; gy_ < gh; gy_ += kPrepBH) sobel(gy_, threadIdx.x);
+        {
+            const int extra = gw - kPrepTW;
+            for (int e = tid; e < extra * gh; e += kPrepTW * kPrepBH) sobel(e / extra, kPrepTW + e % extra);
         }
         __syncthreads();
         for (int ry = threadIdx.y; ry < gh; ry += kPrepBH) {  // row maxima: one output column per thread
