@@ -200,10 +200,14 @@ __device__ __forceinline__ float blend_pow(float w, float e)
     return powf(w, e);
 }
 
-template <bool MATERIALISE>
+// MATERIALISE: 0 = blend only; 1 = any of the reference's per-view tensors; 2 = only uv_aoi_cos / uv_depth_grad, which
+// is what CameraProjection(return_dict=True) asks for (no view-mask tap for invalid texel-views, no pointer tests
+// for the other seven tensors).
+template <int MATERIALISE>
 __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
 {
-    constexpr bool materialise = MATERIALISE;
+    constexpr bool materialise = MATERIALISE != 0;
+    constexpr bool light = MATERIALISE == 2;
     extern __shared__ float s_cam[];  // [Nv,16] mvp, then [Nv] exponent
     wr_pdl_wait();   // dependent launch behind k_view_prep
     wr_pdl_trigger();
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
                 att = sample4(reinterpret_cast<const float4 *>(A.attr_map) + v * npix, t, A.W, A.H);
             if (A.use_depth_grad) valid = valid && (att.w < A.depth_grad_thresh);
             float mp = 0.f;
-            if (A.view_masks && (valid || materialise)) {
+            if (A.view_masks && (valid || (materialise && !light))) {
                 mp = sample1(A.view_masks + v * npix, t, A.W, A.H);
                 valid = valid && (mp > A.mask_thresh);
             }
@@ -256,7 +260,11 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
             sw = sw + wgt;
             sr = sr + att.x * wgt; sg = sg + att.y * wgt; sb = sb + att.z * wgt;
             nvalid += valid ? 1 : 0;
-            if (materialise) {
+            if (light) {
+                const size_t ov = (size_t)v * ntex + o;
+                if (A.uv_aoi_cos) A.uv_aoi_cos[ov] = geo.w;
+                if (A.uv_depth_grad) A.uv_depth_grad[ov] = att.w;
+            } else if (materialise) {
                 const size_t ov = (size_t)v * ntex + o;
                 if (A.uv_pos_ndc) { A.uv_pos_ndc[2 * ov] = gx; A.uv_pos_ndc[2 * ov + 1] = gy; }
                 if (A.uv_pos_proj) { A.uv_pos_proj[3 * ov] = geo.x; A.uv_pos_proj[3 * ov + 1] = geo.y; A.uv_pos_proj[3 * ov + 2] = geo.z; }
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
                 if (A.uv_weight) A.uv_weight[ov] = wgt;
             }
         }
-        if (materialise && A.uv_weight) {  // ExponentialBlend "linear": w / clamp(sum w, 1e-5), clamp [0,1]
+        if (materialise && !light && A.uv_weight) {  // ExponentialBlend "linear": w / clamp(sum w, 1e-5), clamp [0,1]
             const float den = fmaxf(sw, 1e-5f);
             for (int v = 0; v < A.Nv; ++v) {
                 const size_t ov = (size_t)v * ntex + o;
@@ -563,8 +571,12 @@ extern "C" int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void 
     const long long ntex = (long long)A.Hu * A.Wu;
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_uv_unproject");
-    if (materialise) wr_launch_s(k_uv_unproject<true>, dim3(wr_div_up(ntex, 256)), dim3(256), smem, stream, !ctx->profiling, A);
-    else wr_launch_s(k_uv_unproject<false>, dim3(wr_div_up(ntex, 256)), dim3(256), smem, stream, !ctx->profiling, A);
+    const bool heavy = A.uv_pos_ndc || A.uv_pos_proj || A.uv_pos_error || A.uv_attr_proj || A.uv_mask_proj || A.uv_valid ||
+                       A.uv_weight;
+    const dim3 grid(wr_div_up(ntex, 256)), block(256);
+    if (heavy) wr_launch_s(k_uv_unproject<1>, grid, block, smem, stream, !ctx->profiling, A);
+    else if (materialise) wr_launch_s(k_uv_unproject<2>, grid, block, smem, stream, !ctx->profiling, A);
+    else wr_launch_s(k_uv_unproject<0>, grid, block, smem, stream, !ctx->profiling, A);
     WR_CHECK_LAUNCH(ctx, "k_uv_unproject");
     wr_stage(ctx, stream, "end");
     return WR_OK;
