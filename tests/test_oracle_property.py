@@ -60,3 +60,35 @@ def test_views_are_independent(tris, H):
     np.testing.assert_array_equal(i[0], i0[0])
     np.testing.assert_array_equal(i[1], i1[0])
     np.testing.assert_array_equal(r[1], r1[0])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# atlas post-processing: the C statement (wr_oracle_blend.c) against its independent NumPy / Python twin
+# ------------------------------------------------------------------------------------------------------------
+from oracle import blend_numpy  # noqa: E402
+
+_img_shape = st.tuples(st.integers(min_value=1, max_value=14), st.integers(min_value=1, max_value=14))
+
+
+@settings(max_examples=40, deadline=None)
+@given(_img_shape, st.integers(min_value=0, max_value=2 ** 31 - 1), st.integers(min_value=0, max_value=12),
+       st.sampled_from(["src", "max", "avg"]))
+def test_poisson_c_oracle_equals_numpy_twin(shape, seed, iters, mode):
+    H, W = shape
+    rng = np.random.default_rng(seed)
+    src = (rng.random((H, W, 3)) * 1.5 - 0.25).astype(np.float32)
+    tgt = rng.random((H, W, 3)).astype(np.float32)
+    mask = rng.random((H, W)) < 0.6
+    np.testing.assert_array_equal(shim.poisson_blend(src, mask, tgt, iters, mode),
+                                  blend_numpy.poisson_blend(src, mask, tgt, iters, mode))
+
+
+@settings(max_examples=40, deadline=None)
+@given(_img_shape, st.integers(min_value=0, max_value=2 ** 31 - 1), st.integers(min_value=0, max_value=4),
+       st.floats(min_value=0.0, max_value=1.0))
+def test_inpaint_c_oracle_equals_python_twin(shape, seed, radius, known):
+    H, W = shape
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    mask = rng.random((H, W)) >= known
+    np.testing.assert_array_equal(shim.inpaint_u8(img, mask, radius), blend_numpy.inpaint_u8(img, mask, radius))
