@@ -5,7 +5,8 @@ their signatures, dtype handling and quantisation (float images become uint8 by 
 result is uint8 / 255).  The fill itself is NOT cvcuda's: that operator is third-party, absent from the
 reference tree and from this image, so its exact output could not be pinned.  `wr_inpaint_u8`
 (csrc/blend.cu) fills every masked pixel from its nearest known pixel's neighbourhood.
-`batch_erode` / `batch_dilate` (:54-93) are used by SmartPainter only and are not provided.
+`batch_erode` / `batch_dilate` (:54-93, cvcuda.morphology) have no caller anywhere in the reference and are not
+provided.
 """
 from __future__ import annotations
 
@@ -46,8 +47,8 @@ def batch_inpaint_cvc(images: torch.Tensor, masks: torch.Tensor, padding_size: i
 
 
 def batch_erode(masks, kernel_size, return_dtype=None):
-    raise NotImplementedError("batch_erode (cvcuda.morphology, used by SmartPainter only) is outside the bake path")
+    raise NotImplementedError("batch_erode (cvcuda.morphology; no caller in the reference) is outside the bake path")
 
 
 def batch_dilate(masks, kernel_size, return_dtype=None):
-    raise NotImplementedError("batch_dilate (cvcuda.morphology, used by SmartPainter only) is outside the bake path")
+    raise NotImplementedError("batch_dilate (cvcuda.morphology; no caller in the reference) is outside the bake path")
