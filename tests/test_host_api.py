@@ -213,3 +213,46 @@ def test_product_code_never_imports_the_oracle():
         assert "import oracle" not in text and "from oracle" not in text and "libwr_oracle" not in text, path
     for path in glob.glob(os.path.join(ROOT, "worldrenderer_b200", "csrc", "*")):
         assert "oracle" not in open(path).read().replace("oracle/", "").lower() or True
+
+
+def test_poisson_solver_host_logic():
+    from worldrenderer_b200.blend import PoissonBlendingSolver
+    with pytest.raises(ValueError):
+        PoissonBlendingSolver("cupy", "cuda:0")                 # unknown backend: checked before any device work
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            PoissonBlendingSolver("torch-native", "cpu")        # no CPU path
+    probe = object.__new__(PoissonBlendingSolver)               # sweep-count rule needs no device
+    for backend, want in (("torch-native", [0, 1, 2, 9, 1000]), ("torch-cuda", [0, 0, 2, 8, 1000]),
+                          ("triton", [0, 0, 2, 8, 1000])):
+        probe.backend = backend
+        assert [probe._sweeps(n) for n in (0, 1, 2, 9, 1000)] == want   # blend.py:88-100, 166-169, 176-183
+
+
+def test_cv_ops_and_smart_paint_host_side():
+    from worldrenderer_b200 import cv_ops
+    from worldrenderer_b200.smart_paint import candidate_cameras
+    with pytest.raises(NotImplementedError):
+        cv_ops.batch_erode(torch.zeros(1, 4, 4), 3)
+    with pytest.raises(NotImplementedError):
+        cv_ops.batch_dilate(torch.zeros(1, 4, 4), 3)
+    torch.manual_seed(0)
+    cams = candidate_cameras("cpu")                             # smart_paint.py:64-92: 9 elevations x 12 azimuths
+    assert len(cams) == 108 and cams.mvp_mtx.shape == (108, 4, 4)
+    d = cams.cam_pos.norm(dim=-1)
+    assert torch.allclose(d, torch.full_like(d, 1.2), atol=1e-5)  # the perturbation only consumes RNG (camera.py:170-178)
+    torch.manual_seed(0)
+    plain = wr.get_camera(elevation_deg=[-60.0], azimuth_deg=[0.0], distance=[1.2], fovy_deg=[40.0])
+    assert torch.allclose(plain.mvp_mtx[0], cams.mvp_mtx[0])
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            cv_ops.inpaint_cvc(torch.zeros(4, 4, 3), torch.zeros(4, 4), 3)   # CPU tensors: no fallback
+
+
+def test_camera_projection_needs_a_solver_for_poisson_blending():
+    import inspect
+    from worldrenderer_b200.projection import CameraProjection
+    sig = inspect.signature(CameraProjection.__call__)
+    # the reference's defaults are kept (projection.py:54-83): Poisson blending and seam padding are ON by default
+    assert sig.parameters["poisson_blending"].default is True and sig.parameters["uv_padding"].default is True
+    assert sig.parameters["pb_num_iters"].default == 1000 and sig.parameters["uv_size"].default == 2048
