@@ -647,7 +647,11 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
 #define WR_SETUP_LPT4 1
 #endif
             if (WR_SETUP_LPT4 && (long long)F * 4 <= (long long)H * W)
-                wr_launch(k_setup_triangles<4>, dim3(wr_div_up((long long)F * 4, 256), B), dim3(256), stream, pdl, P, 0);
+#ifndef WR_SETUP_LPT
+#define WR_SETUP_LPT 4
+#endif
+                wr_launch(k_setup_triangles<WR_SETUP_LPT>, dim3(wr_div_up((long long)F * WR_SETUP_LPT, 256), B), dim3(256),
+                          stream, pdl, P, 0);
             else
                 wr_launch(k_setup_triangles<1>, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0);
             WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
