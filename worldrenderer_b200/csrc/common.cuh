@@ -98,6 +98,7 @@ struct RasterResult {
     unsigned long long *packed;  // [B,H,W]
     size_t packed_bytes;
     int32_t *view_stats;         // [B,4] zero-initialised ints the caller may use
+    int filled;                  // the FillJob handed to wr_run_raster has been written by the set-up kernel
 };
 
 // The kernel that reads `packed` resets every pixel it consumes to WR_EMPTY_PIXEL; after its launch the
@@ -118,11 +119,76 @@ static inline size_t wr_vertex_pack_bytes(int V, int Vn, bool normals)
     return (((size_t)(V > 0 ? V : 1) * 16 + 255) & ~(size_t)255) + (normals ? (size_t)(Vn > 0 ? Vn : 1) * 16 : 0);
 }
 
+// Background prefill.  The shading pass of a render is bound by its output writes (33 B per pixel, most of them
+// background constants), the triangle set-up pass before it by instruction issue with the memory system idle.  A
+// FillJob describes the constant background of every output map as up to five segments of 16-byte words with a
+// 3-word period (a [.., 3] f32 map repeats every 3 words); the set-up kernel's blocks each write one contiguous
+// share of it before they start their own work, so the background goes out to HBM UNDER the set-up pass, and the
+// shading kernel then stores covered pixels only.
+#define WR_FILL_MAX_SEGS 5
+struct FillSeg {
+    uint4 *ptr;                  // 16-byte aligned
+    unsigned n16;                // 16-byte words (< 2^32)
+    unsigned chunk;              // words per participating block (set by wr_fill_plan)
+    int uniform;                 // pat[0] == pat[1] == pat[2]
+    uint4 pat[3];                // word w of the segment holds pat[w % 3]
+};
+struct FillJob {
+    int nseg;
+    unsigned long long total16;
+    unsigned stride;             // block b participates iff b % stride == 0, as share b / stride (set by wr_fill_plan)
+    unsigned shares;
+    FillSeg seg[WR_FILL_MAX_SEGS];
+};
+
+// Splits the job over the blocks of the kernel that will carry it: every `stride`-th block writes a share of at
+// least ~2048 words (8 per thread of a 256-thread block), so the other blocks pay one compare.
+static inline void wr_fill_plan(FillJob *J, unsigned nblocks)
+{
+    if (J->nseg == 0 || nblocks == 0) return;
+    unsigned long long want = J->total16 / 2048;
+    if (want < 1) want = 1;
+    J->stride = want >= nblocks ? 1u : (unsigned)(nblocks / want);
+    J->shares = (nblocks + J->stride - 1) / J->stride;
+    for (int s = 0; s < J->nseg; ++s) J->seg[s].chunk = (J->seg[s].n16 + J->shares - 1) / J->shares;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void wr_fill_share(const FillJob &J, unsigned bid)
+{
+    if (J.nseg == 0 || bid % J.stride != 0) return;
+    const unsigned share = bid / J.stride;
+#pragma unroll 1
+    for (int s = 0; s < J.nseg; ++s) {
+        const unsigned chunk = J.seg[s].chunk, n16 = J.seg[s].n16;
+        const unsigned long long lo64 = (unsigned long long)share * chunk;
+        if (lo64 >= n16) continue;
+        const unsigned lo = (unsigned)lo64;
+        const unsigned hi = (n16 - lo < chunk) ? n16 : lo + chunk;
+        uint4 *dst = J.seg[s].ptr;
+        const uint4 p0 = J.seg[s].pat[0];
+        if (J.seg[s].uniform) {
+            for (unsigned w = lo + threadIdx.x; w < hi; w += blockDim.x) __stcs(dst + w, p0);
+        } else {
+            const uint4 p1 = J.seg[s].pat[1], p2 = J.seg[s].pat[2];
+            unsigned w = lo + threadIdx.x;
+            unsigned m = w % 3u;
+            const unsigned step = blockDim.x % 3u;
+            for (; w < hi; w += blockDim.x) {
+                __stcs(dst + w, m == 0 ? p0 : (m == 1 ? p1 : p2));
+                m += step;
+                if (m >= 3u) m -= 3u;
+            }
+        }
+    }
+}
+#endif
+
 int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream);
 int wr_set_cuda_error(wr_ctx *ctx, cudaError_t e, const char *where);
 int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
                   int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream,
-                  VertexPack *pack = nullptr);
+                  VertexPack *pack = nullptr, const FillJob *fill = nullptr);
 
 // Programmatic dependent launch (sm_90+): a kernel launched with the attribute may be scheduled while its
 // predecessor on the stream is still draining; it must execute wr_pdl_wait() before touching anything the

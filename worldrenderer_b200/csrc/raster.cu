@@ -40,6 +40,39 @@ __device__ __forceinline__ int floor_div16(int a) { return a >> 4; }
 __device__ __forceinline__ int ceil_div16(int a) { return -((-a) >> 4); }
 __device__ __forceinline__ bool top_left(int dx, int dy) { return dy < 0 || (dy == 0 && dx > 0); }
 
+// DESIGN.md 3.2b for one clip-space vertex: perspective divide, snap to 1/16 px, outcodes.
+// w == 1 exactly (orthographic rows 0 0 0 1): rw == 1 and (a * 1) == a, so the divide and the three
+// multiplications are skipped without changing a bit.
+__device__ __forceinline__ SnapVert snap_one(const float4 c, int W, int H)
+{
+    SnapVert s;
+    s.x = 0; s.y = 0; s.zw = 0.0f;
+    uint32_t flags = 0;
+    if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w)) flags |= WR_SV_FINITE;
+    uint32_t oc = 0;
+    oc |= (c.x < -c.w) ? 1u : 0u;
+    oc |= (c.x > c.w) ? 2u : 0u;
+    oc |= (c.y < -c.w) ? 4u : 0u;
+    oc |= (c.y > c.w) ? 8u : 0u;
+    oc |= (c.z < -c.w) ? 16u : 0u;
+    oc |= (c.z > c.w) ? 32u : 0u;
+    flags |= oc << WR_SV_OC_SHIFT;
+    if (c.w > 0.0f) {
+        const bool unit_w = c.w == 1.0f;
+        const float rw = unit_w ? 1.0f : 1.0f / c.w;
+        const float fx = unit_w ? (c.x * (float)(8 * W)) : (c.x * (float)(8 * W)) * rw;
+        const float fy = unit_w ? (c.y * (float)(8 * H)) : (c.y * (float)(8 * H)) * rw;
+        if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
+            s.x = __float2int_rn(fx) + (8 * W - 8);   // relative to the sample of pixel (0, 0): see SnapVert
+            s.y = __float2int_rn(fy) + (8 * H - 8);
+            s.zw = c.z * rw;
+            flags |= WR_SV_OK;
+        }
+    }
+    s.flags = flags;
+    return s;
+}
+
 // Both snap kernels also clear the per-view counter / depth-range block (consumed by the kernels launched after
 // them on the same stream), which saves a separate memset launch.
 __global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, int W, int H, SnapVert *sv, int *stats,
@@ -50,32 +83,8 @@ __global__ void __launch_bounds__(256) k_snap_vertices(VtxSrc src, int view0, in
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + view0;
     if (v >= src.V) return;
-    const float4 p = wr_load_clip(src, b, v);
-    SnapVert s;
-    s.x = 0; s.y = 0; s.zw = 0.0f;
-    uint32_t flags = 0;
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(p.w)) flags |= WR_SV_FINITE;
-    uint32_t oc = 0;
-    oc |= (p.x < -p.w) ? 1u : 0u;
-    oc |= (p.x > p.w) ? 2u : 0u;
-    oc |= (p.y < -p.w) ? 4u : 0u;
-    oc |= (p.y > p.w) ? 8u : 0u;
-    oc |= (p.z < -p.w) ? 16u : 0u;
-    oc |= (p.z > p.w) ? 32u : 0u;
-    flags |= oc << WR_SV_OC_SHIFT;
-    if (p.w > 0.0f) {
-        const float rw = 1.0f / p.w;
-        const float fx = (p.x * (float)(8 * W)) * rw;
-        const float fy = (p.y * (float)(8 * H)) * rw;
-        if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
-            s.x = __float2int_rn(fx) + (8 * W - 8);   // relative to the sample of pixel (0, 0): see SnapVert
-            s.y = __float2int_rn(fy) + (8 * H - 8);
-            s.zw = p.z * rw;
-            flags |= WR_SV_OK;
-        }
-    }
-    s.flags = flags;
-    reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<int4 *>(&s);
+    const SnapVert s = snap_one(wr_load_clip(src, b, v), W, H);
+    reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<const int4 *>(&s);
 }
 
 __device__ __forceinline__ SnapVert load_sv(const SnapVert *sv, size_t i)
@@ -155,22 +164,69 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
 // fourth row of its bounding box; the bound for in-thread rasterisation grows to 4 x kSmallMaxPix samples, which
 // also keeps such triangles out of the warp-per-triangle queue.  All LPT lanes read the same indices and snapped
 // vertices (same sectors), lane 0 of the group does the queue append.
+// Classification of one (view, triangle) from its three snapped vertices: culled, rasterised
+// right here (small), or to be queued (push = 1 medium, 2 large / to be clipped; entry = queue word).
 template <int LPT>
-__global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0)
+__device__ __forceinline__ void setup_one(const RasterParams &P, const SnapVert &a, const SnapVert &c, const SnapVert &d,
+                                          int t, int sub, unsigned long long *depth_view, int &push, uint32_t &entry)
+{
+    const int W = P.W, H = P.H;
+    const uint32_t f_and = a.flags & c.flags & d.flags;
+    // one test for the common case: all three vertices finite and snapped, no frustum plane has all three
+    // outside; everything else (culled, or to be clipped by the queue pass) takes the cold branch
+    constexpr uint32_t kFastMask = WR_SV_FINITE | WR_SV_OK | (63u << WR_SV_OC_SHIFT);
+    if ((f_and & kFastMask) != (WR_SV_FINITE | WR_SV_OK)) {
+        if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0 && sub == 0) {
+            push = 2;
+            entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
+        }
+        return;
+    }
+    const int x0 = a.x, y0 = a.y, x1 = c.x, y1 = c.y, x2 = d.x, y2 = d.y;
+    const float z0 = a.zw, z1 = c.zw, z2 = d.zw;
+    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+    // pixel (c, r) samples (16 c, 16 r); ceil(a / 16) == (a + 15) >> 4 with an arithmetic shift
+    const int c0 = max((xmin + 15) >> 4, 0), c1 = min(xmax >> 4, W - 1);
+    const int r0 = max((ymin + 15) >> 4, 0), r1 = min(ymax >> 4, H - 1);
+    if (c0 > c1 || r0 > r1) return;
+    const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);  // <= 8192^2: fits int32
+    if (xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
+        // extent below 2^10 sub-pixel units: the doubled area fits int32 exactly
+        const int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
+        if (area2 != 0) {
+            if (npix <= kSmallMaxPix * LPT) {
+                if (r0 + sub <= r1)
+                    raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0, c1, r0 + sub, r1,
+                                 LPT, W, H, depth_view, area2);
+            } else if (sub == 0) {  // cannot happen for 64-px extents; kept for other thresholds
+                push = (npix <= kMediumMaxPix) ? 1 : 2;
+                entry = (uint32_t)(t + P.tri_base);
+            }
+        }
+    } else if (sub == 0) {
+        const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+        if (area2 != 0) {
+            push = (npix <= kMediumMaxPix) ? 1 : 2;
+            entry = (uint32_t)(t + P.tri_base);
+        }
+    }
+}
+
+template <int LPT>
+__global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int view0, const __grid_constant__ FillJob fill)
 {
     wr_pdl_wait();
     wr_pdl_trigger();
+    wr_fill_share(fill, blockIdx.y * gridDim.x + blockIdx.x);
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int t = gt / LPT;
     const int sub = gt % LPT;
     const int b = blockIdx.y + view0;
-    const int W = P.W, H = P.H;
     const unsigned lane = threadIdx.x & 31;
     int push = 0;  // 0 none, 1 medium, 2 large
     uint32_t entry = 0;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0, x2 = 0, y2 = 0, c0 = 0, c1 = 0, r0 = 0, r1 = 0;
-    float z0 = 0.f, z1 = 0.f, z2 = 0.f;
-    unsigned long long *depth_view = P.depth + (size_t)b * H * W;
+    unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
     const unsigned vb = (unsigned)b * (unsigned)P.V;  // B * V < 2^31 (checked by the launcher): 32-bit record index
 
     if (t < P.F) {
@@ -179,49 +235,7 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
         if ((unsigned)i0 < (unsigned)P.V && (unsigned)i1 < (unsigned)P.V && (unsigned)i2 < (unsigned)P.V) {
             const SnapVert a = load_sv32(P.sv, vb + (unsigned)i0), c = load_sv32(P.sv, vb + (unsigned)i1),
                            d = load_sv32(P.sv, vb + (unsigned)i2);
-            const uint32_t f_and = a.flags & c.flags & d.flags;
-            // one test for the common case: all three vertices finite and snapped, no frustum plane has all three
-            // outside; everything else (culled, or to be clipped by the queue pass) takes the cold branch
-            constexpr uint32_t kFastMask = WR_SV_FINITE | WR_SV_OK | (63u << WR_SV_OC_SHIFT);
-            if ((f_and & kFastMask) != (WR_SV_FINITE | WR_SV_OK)) {
-                if ((f_and & WR_SV_FINITE) && ((f_and >> WR_SV_OC_SHIFT) & 63u) == 0 && sub == 0) {
-                    push = 2;
-                    entry = (uint32_t)(t + P.tri_base) | WR_QUEUE_SLOW;
-                }
-            } else {
-                {
-                    x0 = a.x; y0 = a.y; x1 = c.x; y1 = c.y; x2 = d.x; y2 = d.y;
-                    z0 = a.zw; z1 = c.zw; z2 = d.zw;
-                    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
-                    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
-                    // pixel (c, r) samples (16 c, 16 r); ceil(a / 16) == (a + 15) >> 4 with an arithmetic shift
-                    c0 = max((xmin + 15) >> 4, 0); c1 = min(xmax >> 4, W - 1);
-                    r0 = max((ymin + 15) >> 4, 0); r1 = min(ymax >> 4, H - 1);
-                    if (c0 <= c1 && r0 <= r1) {
-                        const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);  // <= 8192^2: fits int32
-                        if (xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent) {
-                            // extent below 2^10 sub-pixel units: the doubled area fits int32 exactly
-                            const int area2 = (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0);
-                            if (area2 != 0) {
-                                if (npix <= kSmallMaxPix * LPT) {
-                                    if (r0 + sub <= r1)
-                                        raster_small(x0, y0, x1, y1, x2, y2, z0, z1, z2, (uint32_t)(t + P.tri_base), c0,
-                                                     c1, r0 + sub, r1, LPT, W, H, depth_view, area2);
-                                } else if (sub == 0) {  // cannot happen for 64-px extents; kept for other thresholds
-                                    push = (npix <= kMediumMaxPix) ? 1 : 2;
-                                    entry = (uint32_t)(t + P.tri_base);
-                                }
-                            }
-                        } else if (sub == 0) {
-                            const long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
-                            if (area2 != 0) {
-                                push = (npix <= kMediumMaxPix) ? 1 : 2;
-                                entry = (uint32_t)(t + P.tri_base);
-                            }
-                        }
-                    }
-                }
-            }
+            setup_one<LPT>(P, a, c, d, t, sub, depth_view, push, entry);
         }
     }
     // warp-aggregated queue append: medium from the front, large / slow from the back
@@ -279,34 +293,318 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
         c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
         c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
         c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
-        SnapVert s;
-        s.x = 0; s.y = 0; s.zw = 0.0f;
-        uint32_t flags = 0;
-        if (isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w)) flags |= WR_SV_FINITE;
-        uint32_t oc = 0;
-        oc |= (c.x < -c.w) ? 1u : 0u;
-        oc |= (c.x > c.w) ? 2u : 0u;
-        oc |= (c.y < -c.w) ? 4u : 0u;
-        oc |= (c.y > c.w) ? 8u : 0u;
-        oc |= (c.z < -c.w) ? 16u : 0u;
-        oc |= (c.z > c.w) ? 32u : 0u;
-        flags |= oc << WR_SV_OC_SHIFT;
-        if (c.w > 0.0f) {
-            // w == 1 exactly (orthographic rows 0 0 0 1): rw == 1 and (a * 1) == a, so the divide and the three
-            // multiplications can be skipped without changing a bit
-            const bool unit_w = c.w == 1.0f;
-            const float rw = unit_w ? 1.0f : 1.0f / c.w;
-            const float fx = unit_w ? (c.x * (float)(8 * W)) : (c.x * (float)(8 * W)) * rw;
-            const float fy = unit_w ? (c.y * (float)(8 * H)) : (c.y * (float)(8 * H)) * rw;
-            if (fabsf(fx) <= WR_COORD_LIMIT && fabsf(fy) <= WR_COORD_LIMIT) {
-                s.x = __float2int_rn(fx) + (8 * W - 8);
-                s.y = __float2int_rn(fy) + (8 * H - 8);
-                s.zw = c.z * rw;
-                flags |= WR_SV_OK;
+        const SnapVert s = snap_one(c, W, H);
+        reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<const int4 *>(&s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-view fast path of the fused render (meshes of small triangles, viewports up to 2048^2).
+//
+// The vertex pass leaves two words per (vertex, view), all views of a vertex side by side:
+//     xy[v * Bq + b] = x_u | y_u << 16          zw[v * Bq + b] = z/w                Bq = B rounded up to even
+// x_u, y_u are the snapped coordinates of DESIGN.md 3.2 relative to an origin that is a whole number of pixels,
+// biased by +32768 so that both halves are unsigned: pixel (c, r) samples x_u = 16 (c + lo_c), y_u = 16 (r + lo_r)
+// with lo_c = 2048 - W/2, lo_r = 2048 - H/2, i.e. the viewport centre sits in the middle of the 16-bit range and
+// +-1875 pixels around it are representable.  A vertex that is not finite, has w <= 0, lies outside the near / far
+// planes or outside that range gets the SENTINEL xy = 0; a triangle with such a vertex takes the cold path, which
+// recomputes the full 16-byte snapped vertices from the source and runs setup_one (the contract's one and only
+// statement of culling / clipping) -- so the compact records can never change a result.
+//
+// k_setup_mv: one thread per TRIANGLE.  The three indices are read once for all views; per pair of views three
+// 8-byte loads fetch the xy words; packed 16-bit min3 / max3 and a handful of SIMD-in-a-word operations decide
+// whether the bounding box holds a sample at all -- most (view, triangle) pairs of a dense mesh end there
+// (~16 instructions instead of ~80 in the per-view kernel).  The pairs that do hold a sample become work items in
+// a per-warp list in shared memory (ballot-compacted, ordered by view and lane) and are then evaluated by ALL
+// lanes of the warp, one item per lane and round, so the lanes of a round are full no matter how few triangles of
+// a view had a sample.  Items whose box holds exactly one sample (the common case for sub-pixel triangles) are
+// evaluated by three integer cross products around that sample; the others walk their box like raster_small.
+constexpr int kMvChunk = 8;            // views classified per compaction round
+constexpr float kRecLimit = 30000.0f;  // |snapped coordinate| (centred) that still gets a record
+constexpr unsigned kGuard = 0x10001000u;
+
+struct MvParams {
+    const unsigned *xy;            // [V][Bq]
+    const float *zw;               // [V][Bq]
+    const int32_t *tri;            // [F,3]
+    int F, V, B, Bq;
+    int W, H;
+    unsigned lo_px, hi_px;         // packed (row << 16 | col) first / last pixel of the viewport in biased pixel units
+    unsigned long long *depth;     // [B,H,W]
+    uint32_t *queue;               // [B,Fq]
+    int Fq;
+    int *counters;                 // [B,4]
+};
+
+__device__ __forceinline__ void snap_rec(const float4 c, int W, int H, int addx, int addy, unsigned &xy, float &zw)
+{
+    // same expressions as snap_one; a record is written only when snap_one would flag the vertex OK | FINITE with
+    // no near / far outcode AND the coordinates fit 16 bits
+    xy = 0u; zw = 0.0f;
+    if (c.w > 0.0f && c.w <= 3.402823466e38f && c.z >= -c.w && c.z <= c.w) {
+        const bool unit_w = c.w == 1.0f;
+        const float rw = unit_w ? 1.0f : 1.0f / c.w;
+        const float fx = unit_w ? (c.x * (float)(8 * W)) : (c.x * (float)(8 * W)) * rw;
+        const float fy = unit_w ? (c.y * (float)(8 * H)) : (c.y * (float)(8 * H)) * rw;
+        if (fabsf(fx) <= kRecLimit && fabsf(fy) <= kRecLimit) {   // false for NaN / inf
+            const int xi = __float2int_rn(fx) + addx, yi = __float2int_rn(fy) + addy;  // in [2760, 62776]
+            xy = (unsigned)xi | ((unsigned)yi << 16);
+            zw = c.z * rw;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int Bq, int W, int H, int addx, int addy, unsigned *xy,
+                                                 float *zw, int *stats, int nstats, VertexPack pack)
+{
+    wr_pdl_trigger();
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
+    constexpr int kStageViews = 32;
+    __shared__ float4 s_mvp[kStageViews * 4];
+    for (int i = threadIdx.x; i < min(B, kStageViews) * 4; i += blockDim.x)
+        s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pack.nrm4 && v < pack.Vn) {
+        const float *n = pack.v_nrm + 3 * (size_t)v;
+        pack.nrm4[v] = make_float4(__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f);
+    }
+    if (v >= src.V) return;
+    const float *p = src.pos + 3 * (size_t)v;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    uint2 *out_xy = reinterpret_cast<uint2 *>(xy + (size_t)v * Bq);
+    float2 *out_zw = reinterpret_cast<float2 *>(zw + (size_t)v * Bq);
+    for (int b0 = 0; b0 < B; b0 += 2) {
+        unsigned rxy[2];
+        float rzw[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int b = b0 + k;
+            rxy[k] = 0u; rzw[k] = 0.0f;
+            if (b < B) {
+                float4 r0, r1, r2, r3;
+                if (b < kStageViews) {
+                    r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
+                } else {
+                    const float4 *m4 = reinterpret_cast<const float4 *>(src.mvp) + 4 * b;
+                    r0 = __ldg(m4); r1 = __ldg(m4 + 1); r2 = __ldg(m4 + 2); r3 = __ldg(m4 + 3);
+                }
+                float4 c;
+                c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
+                c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
+                c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
+                c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
+                snap_rec(c, W, H, addx, addy, rxy[k], rzw[k]);
             }
         }
-        s.flags = flags;
-        reinterpret_cast<int4 *>(sv)[(size_t)b * src.V + v] = *reinterpret_cast<int4 *>(&s);
+        out_xy[b0 >> 1] = make_uint2(rxy[0], rxy[1]);
+        out_zw[b0 >> 1] = make_float2(rzw[0], rzw[1]);
+    }
+}
+
+// Bounding box of a (view, triangle) in biased pixel units, packed (row << 16 | col), clamped to the viewport.
+// t = (last | guard) - first keeps a guard bit per half exactly when last >= first in that half:
+// (t & kGuard) == kGuard  <=>  the box holds a sample;  t == kGuard  <=>  exactly one.
+__device__ __forceinline__ unsigned mv_box(unsigned a, unsigned c, unsigned d, unsigned lo_px, unsigned hi_px,
+                                           unsigned &first)
+{
+    const unsigned mn = __vimin3_u16x2(a, c, d), mx = __vimax3_u16x2(a, c, d);
+    first = __vmaxu2(((mn + 0x000F000Fu) >> 4) & 0x0FFF0FFFu, lo_px);
+    const unsigned last = __vminu2((mx >> 4) & 0x0FFF0FFFu, hi_px);
+    return (last | kGuard) - first;
+}
+
+// Sample exactly on an edge or a vertex (m == 0): the top-left rule of DESIGN.md 3.3 on the orientation-normalised
+// edges.  a_i, b_i: vertex i relative to the sample; F_i: orientation-normalised edge functions.
+__device__ __noinline__ bool mv_tie_break(int a0, int b0, int a1, int b1, int a2, int b2, int F0, int F1, int F2,
+                                          bool flip)
+{
+    int dx0 = a2 - a1, dy0 = b2 - b1, dx1 = a0 - a2, dy1 = b0 - b2, dx2 = a1 - a0, dy2 = b1 - b0;
+    if (flip) { dx0 = -dx0; dy0 = -dy0; dx1 = -dx1; dy1 = -dy1; dx2 = -dx2; dy2 = -dy2; }
+    return (F0 > 0 || top_left(dx0, dy0)) && (F1 > 0 || top_left(dx1, dy1)) && (F2 > 0 || top_left(dx2, dy2));
+}
+
+// One work item whose box holds exactly the sample of pixel (c, r) (viewport coordinates).  Exact integer
+// arithmetic: with a_i = x_i - px, b_i = y_i - py the edge function of edge (v1 -> v2) at the sample is the cross
+// product a1 b2 - a2 b1 (same integer as dx0 (py - y1) - dy0 (px - x1)), and the three add up to the doubled
+// area.  A box with one sample is less than two pixels wide, so everything fits int32 with room to spare.
+// Depth: the expressions of raster_small; for a clockwise triangle raster_small swaps vertices 1 and 2, which
+// negates the edge functions and lets edges 1 and 2 trade places -- reproduced here by the sign of 1 / area and
+// the selects on `flip` (float negation is exact, and the final + 0.0f removes the sign of a zero).
+__device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, unsigned s0,
+                                          unsigned s1, unsigned s2, int b, int c, int r, uint32_t id)
+{
+    const int px = (c + (int)(P.lo_px & 0xFFFFu)) << 4, py = (r + (int)(P.lo_px >> 16)) << 4;
+    const int a0 = (int)(xy0 & 0xFFFFu) - px, b0 = (int)(xy0 >> 16) - py;
+    const int a1 = (int)(xy1 & 0xFFFFu) - px, b1 = (int)(xy1 >> 16) - py;
+    const int a2 = (int)(xy2 & 0xFFFFu) - px, b2 = (int)(xy2 >> 16) - py;
+    const int E0 = a1 * b2 - a2 * b1, E1 = a2 * b0 - a0 * b2, E2 = a0 * b1 - a1 * b0;
+    const int area2 = E0 + E1 + E2;
+    if (area2 == 0) return;
+    const bool flip = area2 < 0;
+    const int F0 = flip ? -E0 : E0, F1 = flip ? -E1 : E1, F2 = flip ? -E2 : E2;
+    const int m = __vimin3_s32(F0, F1, F2);
+    if (m < 0) return;
+    if (m == 0 && !mv_tie_break(a0, b0, a1, b1, a2, b2, F0, F1, F2, flip)) return;
+    const float z0 = __ldg(P.zw + (s0 + b)), z1 = __ldg(P.zw + (s1 + b)), z2 = __ldg(P.zw + (s2 + b));
+    const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
+    const float w0 = __int2float_rn(E0) * inv_area;
+    const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
+    const float w2 = (1.0f - w0) - w1;
+    float zw = ((z0 * w0) + ((flip ? z2 : z1) * w1)) + ((flip ? z1 : z2) * w2);
+    zw = zw + 0.0f;
+    if (zw >= -1.0f && zw <= 1.0f)
+        resolve_sample(P.depth + ((size_t)b * P.H * P.W + (unsigned)(r * P.W + c)), zw, id);
+}
+
+// One work item whose box holds several samples: classify by size, rasterise a small triangle here (the loop of
+// raster_small with the orientation handled by negating the edge vectors), or report it for the queues.
+__device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, unsigned s0,
+                                         unsigned s1, unsigned s2, int b, uint32_t id, int &push)
+{
+    // signed coordinates relative to the sample of viewport pixel (0, 0)
+    const int ox = (int)(P.lo_px & 0xFFFFu) << 4, oy = (int)(P.lo_px >> 16) << 4;
+    const int x0 = (int)(xy0 & 0xFFFFu) - ox, y0 = (int)(xy0 >> 16) - oy;
+    const int x1 = (int)(xy1 & 0xFFFFu) - ox, y1 = (int)(xy1 >> 16) - oy;
+    const int x2 = (int)(xy2 & 0xFFFFu) - ox, y2 = (int)(xy2 >> 16) - oy;
+    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+    const int c0 = max((xmin + 15) >> 4, 0), c1 = min(xmax >> 4, P.W - 1);
+    const int r0 = max((ymin + 15) >> 4, 0), r1 = min(ymax >> 4, P.H - 1);
+    if (c0 > c1 || r0 > r1) return;
+    const int npix = (c1 - c0 + 1) * (r1 - r0 + 1);
+    int dx0 = x2 - x1, dy0 = y2 - y1;  // edge opposite vertex 0
+    int dx1 = x0 - x2, dy1 = y0 - y2;
+    int dx2 = x1 - x0, dy2 = y1 - y0;
+    if (!(xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent && npix <= kSmallMaxPix)) {
+        const long long a2 = (long long)dx2 * (y2 - y0) - (long long)dy2 * (x2 - x0);
+        if (a2 != 0) push = (npix <= kMediumMaxPix) ? 1 : 2;
+        return;
+    }
+    int area2 = dx2 * (y2 - y0) - dy2 * (x2 - x0);  // extent below 2^10: exact in int32
+    if (area2 == 0) return;
+    const bool flip = area2 < 0;
+    if (flip) {
+        dx0 = -dx0; dy0 = -dy0; dx1 = -dx1; dy1 = -dy1; dx2 = -dx2; dy2 = -dy2;
+        area2 = -area2;
+    }
+    const int bias0 = top_left(dx0, dy0) ? 0 : 1;
+    const int bias1 = top_left(dx1, dy1) ? 0 : 1;
+    const int bias2 = top_left(dx2, dy2) ? 0 : 1;
+    const float z0 = __ldg(P.zw + (s0 + b)), z1 = __ldg(P.zw + (s1 + b)), z2 = __ldg(P.zw + (s2 + b));
+    const float za = flip ? z2 : z1, zb = flip ? z1 : z2;
+    const float inv_area = 1.0f / __int2float_rn(area2);
+    const int px0 = 16 * c0, py0 = 16 * r0;
+    int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
+    int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
+    int e2r = dx2 * (py0 - y0) - dy2 * (px0 - x0);
+    unsigned long long *dv = P.depth + (size_t)b * P.H * P.W;
+    unsigned row = (unsigned)(r0 * P.W);
+#pragma unroll 1
+    for (int r = r0; r <= r1; ++r) {
+        int e0 = e0r, e1 = e1r, e2 = e2r;
+#pragma unroll 1
+        for (int cc = c0; cc <= c1; ++cc) {
+            if (e0 >= bias0 && e1 >= bias1 && e2 >= bias2) {
+                const float w0 = __int2float_rn(e0) * inv_area;
+                const float w1 = __int2float_rn(flip ? e2 : e1) * inv_area;
+                const float w2 = (1.0f - w0) - w1;
+                float zw = ((z0 * w0) + (za * w1)) + (zb * w2);
+                zw = zw + 0.0f;
+                if (zw >= -1.0f && zw <= 1.0f) resolve_sample(dv + (row + (unsigned)cc), zw, id);
+            }
+            e0 -= 16 * dy0; e1 -= 16 * dy1; e2 -= 16 * dy2;
+        }
+        e0r += 16 * dx0; e1r += 16 * dx1; e2r += 16 * dx2;
+        row += (unsigned)P.W;
+    }
+}
+
+// queue append of the lanes with push != 0, aggregated per (view, queue) with one atomic each
+__device__ __forceinline__ void mv_push(const MvParams &P, int push, int b, uint32_t entry, unsigned lane)
+{
+    if (__ballot_sync(0xFFFFFFFFu, push != 0) == 0) return;
+    const unsigned key = push ? (unsigned)((b << 1) | (push - 1)) : (0x40000000u | lane);
+    const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (push && (int)lane == leader) base = atomicAdd(P.counters + 4 * b + (push - 1), __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (push) {
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        uint32_t *qv = P.queue + (size_t)b * P.Fq;
+        if (push == 1) qv[slot] = entry;
+        else qv[P.Fq - 1 - slot] = entry;
+    }
+}
+
+// cold (view, triangle) pair: the contract's own classification from the full snapped vertices
+__device__ __noinline__ void mv_cold(const RasterParams &Pold, const VtxSrc &src, int b, int i0, int i1, int i2, int t,
+                                     unsigned long long *depth_view, int &push, uint32_t &entry)
+{
+    const SnapVert a = snap_one(wr_load_clip(src, b, i0), Pold.W, Pold.H);
+    const SnapVert c = snap_one(wr_load_clip(src, b, i1), Pold.W, Pold.H);
+    const SnapVert d = snap_one(wr_load_clip(src, b, i2), Pold.W, Pold.H);
+    setup_one<1>(Pold, a, c, d, t, 0, depth_view, push, entry);
+}
+
+#ifndef WR_MV_MINB
+#define WR_MV_MINB 5
+#endif
+__global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, RasterParams Pold, VtxSrc src,
+                                                              const __grid_constant__ FillJob fill)
+{
+    wr_pdl_wait();
+    wr_pdl_trigger();
+    wr_fill_share(fill, blockIdx.x);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    bool live = t < P.F;
+    int i0 = 0, i1 = 0, i2 = 0;
+    if (live) {
+        i0 = __ldg(P.tri + 3 * (size_t)t); i1 = __ldg(P.tri + 3 * (size_t)t + 1); i2 = __ldg(P.tri + 3 * (size_t)t + 2);
+        live = __vimax3_u32((unsigned)i0, (unsigned)i1, (unsigned)i2) < (unsigned)P.V;
+        if (!live) i0 = i1 = i2 = 0;
+    }
+    // V * Bq < 2^31 (checked by the launcher): 32-bit record indices
+    const unsigned q0 = (unsigned)i0 * (unsigned)P.Bq, q1 = (unsigned)i1 * (unsigned)P.Bq, q2 = (unsigned)i2 * (unsigned)P.Bq;
+    const unsigned lo_px = P.lo_px, hi_px = P.hi_px;
+    const size_t npv = (size_t)P.H * P.W;
+
+    for (int vb = 0; vb < P.B; vb += 2) {
+        uint2 A = make_uint2(0u, 0u), C = A, D = A;
+        if (live) {
+            A = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q0 + vb)));
+            C = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q1 + vb)));
+            D = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q2 + vb)));
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int b = vb + k;
+            if (b >= P.B) break;  // uniform
+            const unsigned a = k ? A.y : A.x, c = k ? C.y : C.x, d = k ? D.y : D.x;
+            unsigned first;
+            const unsigned tt = mv_box(a, c, d, lo_px, hi_px, first);
+            // a vertex without a record has xy == 0 (a record's halves are >= 2760)
+            const bool sentinel = __vimin3_u32(a, c, d) == 0u;
+            int push = 0;
+            uint32_t entry = (uint32_t)t;
+            if (live) {
+                if (sentinel) {
+                    mv_cold(Pold, src, b, i0, i1, i2, t, P.depth + (size_t)b * npv, push, entry);
+                } else if ((tt & kGuard) == kGuard) {
+                    if (tt == kGuard) {
+                        const unsigned rel = first - lo_px;  // no borrow: first >= lo_px in both halves
+                        mv_single(P, a, c, d, q0, q1, q2, b, (int)(rel & 0xFFFFu), (int)(rel >> 16), (uint32_t)t);
+                    } else {
+                        mv_multi(P, a, c, d, q0, q1, q2, b, (uint32_t)t, push);
+                    }
+                }
+            }
+            mv_push(P, push, b, entry, lane);
+        }
     }
 }
 
@@ -484,8 +782,15 @@ __device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc
         const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
                   i2 = __ldg(P.tri + 3 * (size_t)t + 2);
         if (!(entry & WR_QUEUE_SLOW)) {
-            const size_t vb = (size_t)b * P.V;
-            const SnapVert a = load_sv(P.sv, vb + i0), c = load_sv(P.sv, vb + i1), d = load_sv(P.sv, vb + i2);
+            SnapVert a, c, d;
+            if (P.sv) {
+                const size_t vb = (size_t)b * P.V;
+                a = load_sv(P.sv, vb + i0); c = load_sv(P.sv, vb + i1); d = load_sv(P.sv, vb + i2);
+            } else {  // multi-view fast path: no 16-byte snapped vertices in scratch, recompute (same expressions)
+                a = snap_one(wr_load_clip(src, b, i0), P.W, P.H);
+                c = snap_one(wr_load_clip(src, b, i1), P.W, P.H);
+                d = snap_one(wr_load_clip(src, b, i2), P.W, P.H);
+            }
             warp_raster<LARGE>(a.x, a.y, c.x, c.y, d.x, d.y, a.zw, c.zw, d.zw, id, P.W, P.H, depth_view, stripe, lane);
         } else if (LARGE) {
             WarpClipScratch &S = clip_smem[warp];
@@ -579,10 +884,22 @@ __global__ void __launch_bounds__(256) k_resolve_rast(unsigned long long *packed
 // scratch are reserved behind the raster buffers and returned through `extra`.
 int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int F, const int32_t *tri_ranges,
                   int H, int W, size_t extra_bytes, RasterResult *res, void **extra, cudaStream_t stream,
-                  VertexPack *pack)
+                  VertexPack *pack, const FillJob *fill)
 {
+    FillJob no_fill;
+    no_fill.nseg = 0; no_fill.total16 = 0; no_fill.stride = 1; no_fill.shares = 1;
+    FillJob FJ = fill ? *fill : no_fill;
     const int V = src.V;
-    const size_t sv_bytes = wr_align256((size_t)B * (size_t)(V > 0 ? V : 1) * sizeof(SnapVert));
+    // Multi-view fast path (k_snap_mv / k_setup_mv): fused render of a mesh whose triangles are small for this
+    // viewport.  Coarse meshes keep the per-view kernels with several lanes per triangle.
+#ifndef WR_MV
+#define WR_MV 1
+#endif
+    const int Bp = (B + 1) & ~1;
+    const bool use_mv = WR_MV && src.mvp && !tri_ranges && W <= 2048 && H <= 2048 && F > 0 && V > 0 &&
+                        (long long)F * 4 > (long long)H * W && (long long)V * Bp < (1ll << 31);
+    const size_t sv_bytes = use_mv ? wr_align256((size_t)V * Bp * sizeof(int2))
+                                   : wr_align256((size_t)B * (size_t)(V > 0 ? V : 1) * sizeof(SnapVert));
     const size_t depth_bytes = wr_align256((size_t)B * H * W * sizeof(unsigned long long));
     const size_t queue_bytes = wr_align256((size_t)B * (size_t)(F > 0 ? F : 1) * sizeof(uint32_t));
     const size_t stats_bytes = wr_align256((size_t)B * 8 * sizeof(int));
@@ -622,6 +939,7 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
     res->packed = depth;
     res->packed_bytes = packed_bytes;
     res->view_stats = stats + 4 * B;
+    res->filled = (have_work && !tri_ranges && FJ.nseg > 0) ? 1 : 0;
 
     if (have_work) {
         RasterParams P;
@@ -633,6 +951,31 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         // pass drains 1.5 us sooner on config B.
         const int qgrid = ((long long)F * 4 > (long long)H * W) ? (ctx->sm_count + 1) / 2 : ctx->sm_count * 2;
         wr_stage(ctx, stream, "k_snap_vertices");
+        if (use_mv) {
+            MvParams M;
+            unsigned *rec_xy = reinterpret_cast<unsigned *>(sv);
+            float *rec_zw = reinterpret_cast<float *>(rec_xy + (size_t)V * Bp);
+            M.xy = rec_xy; M.zw = rec_zw; M.tri = tri; M.F = F; M.V = V; M.B = B; M.Bq = Bp;
+            M.W = W; M.H = H;
+            const int lo_c = 2048 - W / 2, lo_r = 2048 - H / 2;
+            M.lo_px = (unsigned)lo_c | ((unsigned)lo_r << 16);
+            M.hi_px = (unsigned)(lo_c + W - 1) | ((unsigned)(lo_r + H - 1) << 16);
+            M.depth = depth; M.queue = queue; M.Fq = F; M.counters = stats;
+            P.sv = nullptr;  // the queue pass recomputes the few snapped vertices it needs
+            // stored = snapped (centred) + 8 W - 8 (relative to the sample of pixel 0) + 16 lo_c (bias)
+            k_snap_mv<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
+                src, B, Bp, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec_xy, rec_zw, stats, B * 8, vp);
+            WR_CHECK_LAUNCH(ctx, "k_snap_mv");
+            wr_stage(ctx, stream, "k_setup_triangles");
+            const bool pdl = !ctx->profiling;
+            wr_fill_plan(&FJ, (unsigned)wr_div_up(F, 256));
+            wr_launch(k_setup_mv, dim3(wr_div_up(F, 256)), dim3(256), stream, pdl, M, P, src, FJ);
+            WR_CHECK_LAUNCH(ctx, "k_setup_mv");
+            wr_stage(ctx, stream, "k_raster_queues");
+            wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);
+            WR_CHECK_LAUNCH(ctx, "k_raster_queues");
+            return WR_OK;
+        }
         if (src.mvp)
             k_snap_vertices_allviews<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
                 src, B, W, H, sv, stats, B * 8, vp);
@@ -646,14 +989,16 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
 #ifndef WR_SETUP_LPT4
 #define WR_SETUP_LPT4 1
 #endif
-            if (WR_SETUP_LPT4 && (long long)F * 4 <= (long long)H * W)
 #ifndef WR_SETUP_LPT
 #define WR_SETUP_LPT 4
 #endif
+            const bool lpt4 = WR_SETUP_LPT4 && (long long)F * 4 <= (long long)H * W;
+            wr_fill_plan(&FJ, (unsigned)(wr_div_up((long long)F * (lpt4 ? WR_SETUP_LPT : 1), 256) * B));
+            if (lpt4)
                 wr_launch(k_setup_triangles<WR_SETUP_LPT>, dim3(wr_div_up((long long)F * WR_SETUP_LPT, 256), B), dim3(256),
-                          stream, pdl, P, 0);
+                          stream, pdl, P, 0, FJ);
             else
-                wr_launch(k_setup_triangles<1>, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0);
+                wr_launch(k_setup_triangles<1>, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, P, 0, FJ);
             WR_CHECK_LAUNCH(ctx, "k_setup_triangles");
             wr_stage(ctx, stream, "k_raster_queues");
             wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);
@@ -665,7 +1010,7 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
                 if (count == 0) continue;
                 RasterParams Q = P;
                 Q.tri = tri + 3 * (size_t)start; Q.F = count; Q.tri_base = start;
-                k_setup_triangles<1><<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b);
+                k_setup_triangles<1><<<dim3(wr_div_up(count, 256), 1), 256, 0, stream>>>(Q, b, no_fill);
                 WR_CHECK_LAUNCH(ctx, "k_setup_triangles(range)");
                 k_raster_queues<<<dim3(qgrid, 1), 256, 0, stream>>>(Q, src, b);
                 WR_CHECK_LAUNCH(ctx, "k_raster_queues(range)");

@@ -228,7 +228,8 @@ constexpr int kOutsSimpleDepth = kOutNormal | kOutDepth;                  // mas
 constexpr int kOutsBakeView = kOutGeo | kOutDepth;                        // mask + (pos, aoi_cos) + simple depth
 
 // One column strip of kShadeRows pixels per thread.  grid = (ceil(W/128), ceil(H/kShadeRows), B), 128 threads.
-template <int OUTS, bool PACKED>
+// PRE: the background of every output has been written by the set-up pass (FillJob): covered pixels only.
+template <int OUTS, bool PACKED, bool PRE>
 __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(ShadeParams P)
 {
     const wr_render_args &A = P.a;
@@ -283,7 +284,16 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
     // Strip without a covered pixel in the whole warp (78% of the warps of config B): every lane writes the same
     // constants, so position and normal rows go out as 24 full 16-byte stores each instead of 2 x 3 strided
     // 4-byte stores per lane.  Only the specialised instantiations take it (their output set is known).
-    if (!kGeneric && !has_geo && P.wide_ok) {
+    const float d_bg0 = -(((wz0 * 0.0f + wz1 * 0.0f) + wz2 * 0.0f) + wz3);  // view depth of a background pixel (p = 0)
+    if (PRE) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kShadeRows; ++k) any |= idw[k] != 0xFFFFFFFFu;
+        if (__ballot_sync(0xFFFFFFFFu, any) == 0) {
+            if (two_pass && nrows > 0) lo = d_bg0;
+            goto publish;
+        }
+    } else if (!kGeneric && !has_geo && P.wide_ok) {
         bool any = false;
 #pragma unroll
         for (int k = 0; k < kShadeRows; ++k) any |= idw[k] != 0xFFFFFFFFu;
@@ -327,6 +337,10 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
         for (int j = 0; j + 1 < kShadeRows; ++j) idw[j] = idw[j + 1];  // register rotation: no indexed local array
         idw[kShadeRows - 1] = 0xFFFFFFFFu;
         const bool covered = idk != 0xFFFFFFFFu;
+        if (PRE && !covered) {
+            if (two_pass) lo = fminf(lo, d_bg0);
+            continue;
+        }
         int id = -1;
         PixelGeo g;
         g.px = g.py = g.pz = 0.f;
@@ -505,9 +519,54 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     const bool use_pack = (long long)A.B * A.H * A.W >= 32ll * ((long long)A.V + (want_nrm ? A.Vn : 0));
     pack.pos4 = nullptr;
     pack.nrm4 = nullptr;
+    // Background prefill by the set-up pass (common.cuh FillJob) for the output sets with their own shading
+    // instantiation, when every background value is a constant known now and the maps are 16-byte tileable.
+    FillJob fill;
+    fill.nseg = 0; fill.total16 = 0; fill.stride = 1; fill.shares = 1;
+#ifndef WR_PREFILL
+#define WR_PREFILL 1
+#endif
+    {
+        const bool extras0 = A.out_tri_id || A.out_rast || A.out_attr || A.out_tangent;
+        const bool bg_const = A.out_depth && (A.depth_mode == WR_DEPTH_SIMPLE || A.depth_mode == WR_DEPTH_CONTROLNET ||
+                                              A.depth_mode == WR_DEPTH_ZERO123PP);
+        const bool plain0 = A.out_mask && A.out_pos && A.out_normal && bg_const && !A.out_geo && !extras0;
+        const bool bake0 = A.out_mask && A.out_geo && A.out_depth && A.depth_mode == WR_DEPTH_SIMPLE && !A.out_pos &&
+                           !A.out_normal && !extras0;
+        auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+        auto f2u = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+        auto add = [&](void *ptr, size_t bytes, const uint32_t *period12) {  // period12: 12 words = 3 x uint4
+            FillSeg &sg = fill.seg[fill.nseg++];
+            sg.ptr = static_cast<uint4 *>(ptr);
+            sg.n16 = (unsigned)(bytes / 16);
+            sg.chunk = 0;
+            for (int k = 0; k < 3; ++k) sg.pat[k] = make_uint4(period12[4 * k], period12[4 * k + 1], period12[4 * k + 2], period12[4 * k + 3]);
+            sg.uniform = 1;
+            for (int k = 4; k < 12; ++k) sg.uniform &= period12[k] == period12[k & 3];
+            fill.total16 += sg.n16;
+        };
+        if (WR_PREFILL && (plain0 || bake0) && (npix & 15) == 0 && npix * 16 / 16 < (1ull << 32) && aligned(A.out_mask) && aligned(A.out_depth) &&
+            aligned(A.out_pos) && aligned(A.out_normal) && aligned(A.out_geo)) {
+            uint32_t w[12];
+            for (int k = 0; k < 12; ++k) w[k] = 0;
+            add(A.out_mask, npix, w);
+            for (int k = 0; k < 12; ++k) w[k] = f2u(A.depth_bg);
+            add(A.out_depth, npix * 4, w);
+            if (plain0) {
+                for (int k = 0; k < 12; ++k) w[k] = 0;
+                add(A.out_pos, npix * 12, w);
+                for (int k = 0; k < 12; ++k) w[k] = f2u(A.normal_bg[k % 3]);
+                add(A.out_normal, npix * 12, w);
+            } else {
+                const float aoi_bg = fminf(fmaxf(A.normal_bg[2], 0.0f), 1.0f);
+                for (int k = 0; k < 12; ++k) w[k] = (k & 3) == 3 ? f2u(aoi_bg) : 0u;
+                add(A.out_geo, npix * 16, w);
+            }
+        }
+    }
     int rc = wr_run_raster(ctx, src, A.B, A.tri, A.F, nullptr, A.H, A.W,
                            mask_bytes + (use_pack ? wr_vertex_pack_bytes(A.V, A.Vn, want_nrm) : 0), &res, &extra,
-                           stream, use_pack ? &pack : nullptr);
+                           stream, use_pack ? &pack : nullptr, fill.nseg ? &fill : nullptr);
     if (rc != WR_OK) return rc;
 
     ShadeParams P;
@@ -529,17 +588,24 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
         // dependent launch only when the raster stages were launched (the chain's first kernel is a plain launch)
         const bool pdl = !ctx->profiling && A.F > 0 && A.V > 0;
         const dim3 block(WR_SHADE_THREADS);
+        const bool pre = res.filled != 0;
+#define WR_SHADE_LAUNCH(OUTS, PK) \
+    do { \
+        if (pre) wr_launch(k_shade<OUTS, PK, true>, grid, block, stream, pdl, P); \
+        else wr_launch(k_shade<OUTS, PK, false>, grid, block, stream, pdl, P); \
+    } while (0)
         if (use_pack) {
-            if (plain && two_pass) wr_launch(k_shade<kOutsRenderDefault, true>, grid, block, stream, pdl, P);
-            else if (plain) wr_launch(k_shade<kOutsSimpleDepth, true>, grid, block, stream, pdl, P);
-            else if (bake) wr_launch(k_shade<kOutsBakeView, true>, grid, block, stream, pdl, P);
-            else wr_launch(k_shade<-1, true>, grid, block, stream, pdl, P);
+            if (plain && two_pass) WR_SHADE_LAUNCH(kOutsRenderDefault, true);
+            else if (plain) WR_SHADE_LAUNCH(kOutsSimpleDepth, true);
+            else if (bake) WR_SHADE_LAUNCH(kOutsBakeView, true);
+            else wr_launch(k_shade<-1, true, false>, grid, block, stream, pdl, P);
         } else {
-            if (plain && two_pass) wr_launch(k_shade<kOutsRenderDefault, false>, grid, block, stream, pdl, P);
-            else if (plain) wr_launch(k_shade<kOutsSimpleDepth, false>, grid, block, stream, pdl, P);
-            else if (bake) wr_launch(k_shade<kOutsBakeView, false>, grid, block, stream, pdl, P);
-            else wr_launch(k_shade<-1, false>, grid, block, stream, pdl, P);
+            if (plain && two_pass) WR_SHADE_LAUNCH(kOutsRenderDefault, false);
+            else if (plain) WR_SHADE_LAUNCH(kOutsSimpleDepth, false);
+            else if (bake) WR_SHADE_LAUNCH(kOutsBakeView, false);
+            else wr_launch(k_shade<-1, false, false>, grid, block, stream, pdl, P);
         }
+#undef WR_SHADE_LAUNCH
     }
     WR_CHECK_LAUNCH(ctx, "k_shade");
     wr_raster_consumed(ctx, &res);

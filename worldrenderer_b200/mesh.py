@@ -48,7 +48,7 @@ class TexturedMesh:
     _v_tang: Optional[torch.Tensor] = None
 
     # (name) -> (key, int32 tensor): contiguous int32 copies of the index tensors
-    _i32_cache: Dict[str, Tuple[tuple, torch.Tensor]] = field(default_factory=dict, repr=False, compare=False)
+    _i32_cache: Dict[str, tuple] = field(default_factory=dict, repr=False, compare=False)
 
     # ------------------------------------------------------------------ lazily derived attributes
     @property
@@ -99,10 +99,12 @@ class TexturedMesh:
             src = getattr(self, name)
         key = (src.data_ptr(), src._version, tuple(src.shape), src.dtype, src.device)
         hit = self._i32_cache.get(name)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        # the entry keeps the SOURCE tensor alive and is matched by identity: a replaced index tensor whose storage
+        # the caching allocator hands out again at the same address can never alias a stale copy
+        if hit is not None and hit[1] is src and hit[0] == key:
+            return hit[2]
         out = src.to(torch.int32).contiguous()
-        self._i32_cache[name] = (key, out)
+        self._i32_cache[name] = (key, src, out)
         return out
 
     # ------------------------------------------------------------------ normals / tangents
