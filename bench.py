@@ -17,8 +17,18 @@ JSON keys beyond the base contract:
   cpu_baseline  the oracle port of the reference's render path timed on this box's host cores
   e2e           same metric through the public API with host buffers (H2D of the mesh, D2H of the maps)
   bake          ms per UV bake, config C (6 x 768^2 images -> 1024^2 atlas), device resident: the
-                CameraProjection call of SURVEY 8d, the unprojection kernel alone, and the same call with the
-                reference's default tail (seam padding; padding + 1000 Poisson sweeps)
+                CameraProjection call of SURVEY 8d, the unprojection kernel alone, uv_precompute alone (1024^2 and
+                4096^2), and the same call with the reference's default tail (seam padding; padding + 1000 sweeps)
+  timing        how the timed region ran (launch path, L2 policy); kept out of `config`, which names the workload
+                only and is identical in both arms
+  config_a      config A (50k-face icosphere, same rig): ms per step and views/s on this GPU
+  config_d      config D (BASELINE.json configs[3]): 8 meshes x 6 views per GPU per step, one CUDA-graph replay per
+                step (RenderGraph), whole-job views/s and the ratio to N x the config-B value
+  bake_sharded  config E (BASELINE.json configs[4]): 32 views of 2048^2 of a 5M-face mesh baked into a 4096^2
+                atlas, views sharded over the ranks, accumulators exchanged ("auto" = fused peer-memory /
+                NVSwitch-multicast kernel, "nccl" = all_reduce + finalize); ms per bake, the exchange step alone,
+                equality with a 1-rank bake, and strong-scaling efficiency against the 1-rank time measured on
+                rank 0 in the same run
 
 `--impl reference` times the reference's render path on the host cores.  The reference has no CPU
 implementation of its own (its rasterizer is the GPU-only nvdiffrast), so this arm is the oracle
@@ -153,10 +163,11 @@ def cpu_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_render_step(state, views: int = N_VIEWS):
+def cpu_render_step(state, views: int = N_VIEWS, nthreads: int = 0):
     from oracle import render_oracle
     v, f32, v_nrm, mvp, w2c = state
-    return render_oracle.render(v, f32, mvp[:views], w2c[:views], H, W, v_nrm=v_nrm, nthreads=cpu_threads())
+    return render_oracle.render(v, f32, mvp[:views], w2c[:views], H, W, v_nrm=v_nrm,
+                                nthreads=nthreads or cpu_threads(), elementwise="by_view")
 
 
 def run_reference(args):
@@ -176,10 +187,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, flush=False),
+        "config": workload_config(args.gpus),
+        "timing": {"l2": "n/a (host run)", "launch_path": "n/a (host run)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full steps (6 views 768^2 of the 1M-face mesh each), "
-                                   f"oracle/render_oracle.py over oracle/wr_oracle.c with {cores} OpenMP threads; "
+                                   f"oracle/render_oracle.py over oracle/wr_oracle.c (-O3 -march=native) with {cores} "
+                                   "OpenMP threads, element-wise tail of each view on its own thread; "
                                    "the reference itself has no CPU path (nvdiffrast is GPU-only)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -187,13 +200,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus: int, flush: bool = True):
+def workload_config(n_gpus: int):
+    """Names the workload only -- identical in both arms (how a run was timed goes into `timing`)."""
     return {"workload": "config B: 1M-face procedural terrain (501501 vertices), canonical 6-view orthographic rig, "
                         "768x768, outputs mask+position+depth(controlnet)+normal; one mesh per GPU (seed = rank)",
             "faces": 2 * TERRAIN[0] * TERRAIN[1], "views_per_step": N_VIEWS, "resolution": [H, W],
-            "parallelism": f"by-mesh x{n_gpus}, no collective",
-            "l2": "flushed between timed steps by a 512 MiB device write outside the per-step events" if flush
-                  else "n/a (host run)"}
+            "parallelism": f"by-mesh x{n_gpus}, no collective"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,8 +243,17 @@ def run_ours(args):
     mesh = make_mesh(torch.from_numpy(v_np).to(dev), torch.from_numpy(f_np).to(dev))
     mesh.v_nrm  # vertex normals: once per mesh, like the reference's lazy property
 
-    def step():
+    def step_eager():
         return wr.render(ctx, mesh, cam, H, W, render_attr=False, render_depth=True, render_normal=True)
+
+    # The step of the timed region: the same render() captured once into a CUDA graph (wr.RenderGraph) and replayed
+    # -- one host call per step, so eight ranks sharing one host cannot fall behind their GPUs (--eager times the
+    # plain call instead; `eager_ms_per_step` is reported either way).
+    graph = None if args.eager else wr.RenderGraph(ctx, [(mesh, cam)], H, W, render_attr=False, render_depth=True,
+                                                   render_normal=True)
+
+    def step():
+        return graph.replay()[0] if graph is not None else step_eager()
 
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -267,6 +288,17 @@ def run_ours(args):
     total_ms_max = float(tot.item())
     value = world * N_VIEWS * K / (total_ms_max * 1e-3)
 
+    # ---- the same step issued eagerly (ctypes call per step) ---------------------------------------
+    Ke_ = min(K, 30)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Ke_)]
+    for k in range(Ke_):
+        flush_buf.fill_(k & 0xFF)
+        ev[k][0].record()
+        step_eager()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    eager_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
     # ---- per-kernel stage timing (same steps, library-side events), rank 0 ------------------------
     stages, launches_per_step = {}, 0
     if rank == 0:
@@ -274,7 +306,7 @@ def run_ours(args):
         reps = min(K, 20)
         for k in range(reps):
             flush_buf.fill_(k & 0xFF)
-            step()
+            step_eager()
             for name, ms in ctx.ctx.profile_read():
                 stages.setdefault(name, []).append(ms)
         ctx.ctx.profile(False)
@@ -363,10 +395,14 @@ def run_ours(args):
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = world * N_VIEWS * Ke / float(e2e_dt.item())
 
-    # ---- bake (config C), rank 0 -----------------------------------------------------------------
-    bake = None
+    # ---- bake (config C) and config A, rank 0 ------------------------------------------------------
+    bake, config_a = None, None
     if rank == 0 and not args.no_bake:
         bake = bench_bake(ctx, dev, flush_buf)
+        config_a = bench_config_a(ctx, dev, flush_buf, cam)
+    # ---- config D (8 meshes per GPU per step) and config E (view-sharded bake), all ranks ----------
+    config_d = None if args.no_extra else bench_config_d(dev, rank, world, flush_buf, cam, min(K, 20), value)
+    bake_sharded = None if args.no_extra else bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=not args.small_e)
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -377,7 +413,9 @@ def run_ours(args):
         if dom is not None:
             achieved = ab[dom] * N_VIEWS / (kernel_stages[dom] * 1e-3) / 1e9
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
             if os.path.exists(tpath):
                 with open(tpath) as fh:
                     traffic = json.load(fh).get(dom)  # DRAM bytes per launch of this kernel from the committed ncu capture
@@ -392,6 +430,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "timing": {"l2": "flushed between timed steps by a 512 MiB device write outside the per-step events",
+                       "launch_path": "eager ctypes call per step" if graph is None else
+                       "one CUDA-graph replay per step (wr.RenderGraph capture of the same render() call)",
+                       "eager_ms_per_step": eager_ms},
             "roofline": roofline,
             "pipeline": {"bound": "hbm", "achieved": pipe_achieved, "peak": peak, "unit": "GB/s",
                          "frac": pipe_achieved / peak, "frac_of_nominal_8000": pipe_achieved / 8000.0,
@@ -407,6 +449,9 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
             "bake": bake,
+            "config_a": config_a,
+            "config_d": config_d,
+            "bake_sharded": bake_sharded,
         }
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = bench_cpu_baseline()
@@ -414,6 +459,216 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _timed(torch, flush_buf, fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ms = []
+    for k in range(reps):
+        flush_buf.fill_(k & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms.append(a.elapsed_time(b))
+    return ms
+
+
+def bench_config_a(ctx, dev, flush_buf, cam):
+    """Config A (BASELINE.json configs[0]): 50k-face icosphere, the canonical rig, 768^2."""
+    import torch
+
+    import worldrenderer_b200 as wr
+    from worldrenderer_b200 import synth
+    v, f = synth.icosphere(50, 0.5)
+    mesh = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32, device=dev), t_pos_idx=torch.tensor(f, dtype=torch.int64, device=dev))
+    mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
+    mesh.v_nrm
+    ms = float(np.median(_timed(torch, flush_buf, lambda: wr.render(ctx, mesh, cam, H, W, render_attr=False))))
+    bytes_step = N_VIEWS * (12 * f.shape[0] + 24 * v.shape[0] + 33 * H * W)
+    peak, _ = peaks()
+    return {"workload": "config A: 50k-face icosphere, canonical 6-view rig, 768^2, same outputs as config B",
+            "ms_per_step": ms, "views_per_s": N_VIEWS / (ms * 1e-3), "algorithmic_bytes_per_step": bytes_step,
+            "frac_of_hbm_peak": bytes_step / (ms * 1e-3) / 1e9 / peak}
+
+
+def bench_config_d(dev, rank, world, flush_buf, cam, K, config_b_value):
+    """Config D (BASELINE.json configs[3]): a batch of 8 x world meshes x 6 views at 768^2 sharded by mesh, 8 meshes
+    per GPU and step, no communication.  One step = one RenderGraph replay (8 render() calls)."""
+    import torch
+    import torch.distributed as dist
+
+    import worldrenderer_b200 as wr
+    per_gpu = 8
+    meshes = []
+    for j in range(per_gpu):
+        v_np, f_np = terrain_arrays(rank * per_gpu + j)
+        m = wr.TexturedMesh(v_pos=torch.from_numpy(v_np).to(dev), t_pos_idx=torch.from_numpy(f_np).to(dev))
+        m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+        m.v_nrm
+        meshes.append(m)
+    ctx = wr.NVDiffRastContextWrapper(str(dev), "cuda")
+    g = wr.RenderGraph(ctx, [(m, cam) for m in meshes], H, W, render_attr=False)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for k in range(K):
+        flush_buf.fill_(k & 0xFF)
+        ev[k][0].record()
+        g.replay()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    tot = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms = float(tot.item()) / K
+    value = world * per_gpu * N_VIEWS / (ms * 1e-3)
+    del g, meshes
+    torch.cuda.empty_cache()
+    return {"workload": f"config D: {per_gpu * world} terrain meshes (1M faces each, seeds 0..{per_gpu * world - 1}) x 6 views "
+                        f"at 768^2, {per_gpu} meshes per GPU and step, sharded by mesh, no collective",
+            "meshes_per_gpu": per_gpu, "ms_per_step": ms, "views_per_s": value,
+            "ratio_to_config_b_value": value / config_b_value,
+            "launch_path": "one CUDA-graph replay per step (8 render() calls captured by wr.RenderGraph)"}
+
+
+def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
+    """Config E (BASELINE.json configs[4]): 32 views at 2048^2 of a 5M-face terrain baked into a 4096^2 atlas, the
+    views sharded over the ranks and the weighted accumulators exchanged (the one collective of the path).
+    full=False: the scaled shape (1M faces, 32 x 1024^2 views, 2048^2 atlas)."""
+    import contextlib
+    import io
+
+    import torch
+    import torch.distributed as dist
+
+    import worldrenderer_b200 as wr
+    from worldrenderer_b200 import parallel, synth
+    from worldrenderer_b200.uv import uv_finalize
+
+    NV, RES, UV = (32, 2048, 4096) if full else (32, 1024, 2048)
+    NX, NY = (2500, 1000) if full else TERRAIN
+    v, f = synth.terrain(NX, NY, 0)
+    v = v / np.abs(v).max() * 0.5
+    v = np.ascontiguousarray(np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1), np.float32)
+    f = np.ascontiguousarray(f, np.int64)
+    vt = synth.terrain_uv(NX, NY).astype(np.float32)
+    mesh = wr.TexturedMesh(v_pos=torch.from_numpy(v).to(dev), t_pos_idx=torch.from_numpy(f).to(dev),
+                           v_tex=torch.from_numpy(vt).to(dev), t_tex_idx=torch.from_numpy(f).to(dev),
+                           texture=torch.zeros((UV, UV, 3), device=dev))
+    mesh.set_stitched_mesh(mesh.v_pos, mesh.t_pos_idx)
+    mesh.v_nrm
+    cam = wr.get_orthogonal_camera(elevation_deg=[20.0] * NV, distance=[1.0] * NV, left=-0.55, right=0.55,
+                                   bottom=-0.55, top=0.55, azimuth_deg=list(np.linspace(0, 360, NV + 1)[:-1]),
+                                   device=str(dev))
+
+    def images_for(lo, hi):
+        # img[v, y, x, c] = .5 + .5 sin(w_c . (x, y) + phi_vc), generated on the device (seeded per global view)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        omega = torch.empty(3, 2).uniform_(0.01, 0.06, generator=g).to(dev)
+        phi = torch.empty(NV, 3).uniform_(0.0, 6.2831853, generator=g)[lo:hi].to(dev)
+        y, x = torch.meshgrid(torch.arange(RES, device=dev, dtype=torch.float32),
+                              torch.arange(RES, device=dev, dtype=torch.float32), indexing="ij")
+        arg = omega[None, :, 0, None, None] * x + omega[None, :, 1, None, None] * y + phi[:, :, None, None]
+        return (0.5 + 0.5 * torch.sin(arg)).permute(0, 2, 3, 1).contiguous()
+
+    lo, hi = parallel.shard_bounds(NV, world)[rank]
+    images = images_for(lo, hi)
+    kw = dict(aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1, uv_exp_blend_alpha=3.0)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    solo = dist.new_group([0]) if world > 1 else None   # rank 0 alone: the 1-rank bake of this run
+
+    def time_bake(mode, cam_l, img_l, group_sync=True, reps=8, group=None):
+        kw_ = dict(kw, group=group)
+        for _ in range(2):
+            parallel.sharded_bake(ctx, mesh, cam_l, img_l, UV, exchange=mode, **kw_)
+        if group_sync:
+            sync()
+        else:
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = parallel.sharded_bake(ctx, mesh, cam_l, img_l, UV, exchange=mode, **kw_)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if group_sync and world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    res = {"workload": f"config E{'' if full else ' (scaled)'}: {f.shape[0]} faces, {NV} views of {RES}^2 on a ring, "
+                       f"{UV}^2 atlas, views sharded over {world} rank(s), accumulators exchanged and finalised on every rank",
+           "views": NV, "view_resolution": RES, "atlas": UV, "faces": int(f.shape[0])}
+    with contextlib.redirect_stdout(io.StringIO()):
+        if world == 1:
+            ms, (atlas, any_) = time_bake("auto", cam, images)
+            res.update({"ms_per_bake": ms, "ms_per_bake_1_rank": ms, "covered_texels": int(any_.sum())})
+            bytes_bake = 32 * NV * RES * RES + 38 * UV * UV + NV * (12 * f.shape[0] + 24 * v.shape[0] + 33 * RES * RES)
+            peak, _ = peaks()
+            res["algorithmic_bytes_per_bake"] = bytes_bake
+            res["frac_of_hbm_peak"] = bytes_bake / (ms * 1e-3) / 1e9 / peak
+            return res
+        ms_auto, (atlas, any_) = time_bake("auto", cam[lo:hi], images)
+        atlas, any_ = atlas.clone(), any_.clone()
+        ms_nccl, (atlas_n, any_n) = time_bake("nccl", cam[lo:hi], images)
+        # the exchange step alone, on this bake's accumulators
+        ws = parallel._p2p_workspace(UV, UV, dev, None)
+        exch = {}
+        if ws is not None:
+            old = mesh.texture
+
+            def run_fused():
+                return ws.reduce_finalize(ctx, old)
+
+            def run_nccl():
+                t = ws.accum.clone()
+                parallel.all_reduce_accumulators(t)
+                return uv_finalize(ctx, t, old)
+
+            for name, fn in (("fused", run_fused), ("nccl_all_reduce_plus_finalize", run_nccl)):
+                for _ in range(2):
+                    fn()
+                sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(8):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / 8], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                exch[name] = float(t.item())
+            exch["kernel"] = "k_uv_reduce_finalize_mc (multimem.ld_reduce / multimem.st)" if (ws.mc_ptr and world >= 4) \
+                else "k_uv_reduce_finalize_p2p (peer loads / stores)"
+        # rank 0 bakes all views alone: the 1-rank time of THIS run and the result to compare with
+        same_mask, max_err, ms_one = True, 0.0, None
+        if rank == 0:
+            img_all = images_for(0, NV)
+            ms_one, (atlas1, any1) = time_bake("nccl", cam, img_all, group_sync=False, reps=4, group=solo)
+            same_mask = bool(torch.equal(any1, any_))
+            max_err = float((atlas1 - atlas).abs().max())
+            del img_all
+        sync()
+        gathered = [torch.empty_like(atlas) for _ in range(world)]
+        dist.all_gather(gathered, atlas)
+        identical = all(torch.equal(g, gathered[0]) for g in gathered)
+        res.update({"ms_per_bake": ms_auto, "ms_per_bake_nccl": ms_nccl, "exchange_step_ms": exch,
+                    "ms_per_bake_1_rank": ms_one, "mask_equal_to_1_rank": same_mask, "max_abs_err_vs_1_rank": max_err,
+                    "ranks_identical": identical,
+                    "strong_scaling_efficiency": None if ms_one is None else ms_one / (world * ms_auto),
+                    "nvlink_bytes_per_texel": {"fused_multicast": "20 B out (in-switch sum) + 13 B in", "nccl": "2 x 20 B"}})
+    return res
 
 
 def bench_cpu_baseline():
@@ -425,10 +680,15 @@ def bench_cpu_baseline():
         reps += 1
     dt = time.perf_counter() - t0
     cores = cpu_threads()
+    t1 = time.perf_counter()
+    cpu_render_step(state, nthreads=1)      # single-core figure: one full step on one thread
+    dt1 = time.perf_counter() - t1
     return {"value": N_VIEWS * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{reps} full steps (6 views 768^2, same 1M-face mesh), oracle port of render.py:220-286 "
-                      f"with {cores} OpenMP threads; vertex normals excluded on both sides",
-            "ms_per_step": 1e3 * dt / reps}
+                      f"(C operators -O3 -march=native, {cores} OpenMP threads; NumPy tail of each view on its own "
+                      "thread); vertex normals excluded on both sides",
+            "ms_per_step": 1e3 * dt / reps,
+            "single_core": {"value": N_VIEWS / dt1, "unit": UNIT, "cores": 1, "ms_per_step": 1e3 * dt1}}
 
 
 def bench_bake(ctx, dev, flush_buf):
@@ -504,6 +764,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bake", action="store_true", help="skip the config C bake timing")
+    ap.add_argument("--no-extra", action="store_true", help="skip config D and the config E sharded bake")
+    ap.add_argument("--small-e", action="store_true", help="config E at the scaled shape (1M faces, 32 x 1024^2, 2048^2 atlas)")
+    ap.add_argument("--eager", action="store_true", help="time the eager render() call instead of its CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 40:

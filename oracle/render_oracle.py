@@ -16,6 +16,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional
 
+import os
+
 import numpy as np
 
 from . import shim
@@ -100,7 +102,12 @@ def normalize_depth(depth: np.ndarray, mask: np.ndarray, spec: DepthSpec) -> np.
 def render(v_pos, tri, mvp, w2c, height: int, width: int, v_nrm=None, tri_nrm=None,
            depth: Optional[DepthSpec] = DepthSpec(), normal_background: float = 0.0,
            v_tex=None, tri_tex=None, texture=None, attr_background: float = 0.5,
-           texture_filter_mode: str = "linear", nthreads: int = 0) -> dict:
+           texture_filter_mode: str = "linear", nthreads: int = 0, elementwise: str = "numpy") -> dict:
+    """elementwise="by_view": the element-wise NumPy tail (view depth, normalisers, normal normalisation) of each
+    view runs on its own host thread -- same arithmetic, bit for bit (tests/test_oracle_golden.py).  bench.py uses
+    it for the CPU arm so that the arm scales with the host cores, as the reference's torch code would on CPU."""
+    if elementwise == "by_view" and texture is None:
+        return _render_by_view(v_pos, tri, mvp, w2c, height, width, v_nrm, tri_nrm, depth, normal_background, nthreads)
     v = _a(v_pos)
     tri = np.asarray(tri, np.int32).reshape(-1, 3)
     mvp = _a(mvp).reshape(-1, 4, 4)
@@ -132,6 +139,59 @@ def render(v_pos, tri, mvp, w2c, height: int, width: int, v_nrm=None, tri_nrm=No
         tex_c = shim.interpolate(_a(v_tex)[None], rast, tt, nthreads)          # render.py:261
         fg = shim.texture(_a(texture)[None], tex_c, texture_filter_mode, "wrap", nthreads)  # render.py:267
         out["attr"] = np.where(mask[..., None], fg, f32(attr_background)).astype(f32)      # render.py:268-269
+    return out
+
+
+def _render_by_view(v_pos, tri, mvp, w2c, height, width, v_nrm, tri_nrm, depth, normal_background, nthreads):
+    """render() with the element-wise NumPy tail of every view on its own host thread (NumPy releases the GIL inside
+    its loops).  Per-view minima / maxima make the views independent, so this is the same arithmetic as render(),
+    bit for bit; only the C operators see all views at once."""
+    from concurrent.futures import ThreadPoolExecutor
+    v = _a(v_pos)
+    tri = np.asarray(tri, np.int32).reshape(-1, 3)
+    mvp = _a(mvp).reshape(-1, 4, 4)
+    w2c = _a(w2c).reshape(-1, 4, 4)
+    B = mvp.shape[0]
+    clip = shim.clip_positions(v, mvp, nthreads)
+    rast, ids = shim.rasterize(clip, tri, (height, width), nthreads)
+    pos = shim.interpolate(v[None], rast, tri, nthreads)
+    nrm = None
+    if v_nrm is not None:
+        tn = tri if tri_nrm is None else np.asarray(tri_nrm, np.int32).reshape(-1, 3)
+        nrm = shim.interpolate(_a(v_nrm)[None], rast, tn, nthreads)
+    out = {"rast": rast, "tri_id": ids, "mask": np.empty(rast.shape[:3], bool), "pos": pos}
+    if depth is not None:
+        out["depth_view"] = np.empty(rast.shape[:3], f32)
+        out["depth"] = np.empty(rast.shape[:3], f32)
+    if nrm is not None:
+        out["normal"] = np.empty(nrm.shape, f32)
+
+    def tail(b):
+        mask = rast[b:b + 1, ..., 3] > 0
+        out["mask"][b:b + 1] = mask
+        p = pos[b:b + 1]
+        if depth is not None:
+            m = w2c[b:b + 1, None, None, 2, :]
+            zv = ((m[..., 0] * p[..., 0] + m[..., 1] * p[..., 1]) + m[..., 2] * p[..., 2]) + m[..., 3]
+            d = (-zv).astype(f32)
+            out["depth_view"][b:b + 1] = d
+            lo = d.reshape(1, -1).min(-1)[:, None, None]
+            d = np.where(mask, d, lo).astype(f32)
+            out["depth"][b:b + 1] = normalize_depth(d, mask, depth)
+        if nrm is not None:
+            n = nrm[b:b + 1]
+            ln = np.sqrt(((n[..., 0] * n[..., 0] + n[..., 1] * n[..., 1]) + n[..., 2] * n[..., 2]))
+            n = (n / np.maximum(ln, f32(1e-12))[..., None]).astype(f32)
+            n[~mask] = f32(normal_background)
+            out["normal"][b:b + 1] = n
+
+    workers = max(1, min(B, nthreads if nthreads > 0 else (os.cpu_count() or 1)))
+    if workers == 1:
+        for b in range(B):
+            tail(b)
+    else:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(tail, range(B)))
     return out
 
 

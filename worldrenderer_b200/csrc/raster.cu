@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
 // Multi-view fast path of the fused render (meshes of small triangles, viewports up to 2048^2).
 //
 // The vertex pass leaves two words per (vertex, view), all views of a vertex side by side:
-//     xy[v * Bq + b] = x_u | y_u << 16          zw[v * Bq + b] = z/w                Bq = B rounded up to even
+//     rec[b * V + v] = (x_u | y_u << 16, z/w)          8 bytes, fetched with one load
 // x_u, y_u are the snapped coordinates of DESIGN.md 3.2 relative to an origin that is a whole number of pixels,
 // biased by +32768 so that both halves are unsigned: pixel (c, r) samples x_u = 16 (c + lo_c), y_u = 16 (r + lo_r)
 // with lo_c = 2048 - W/2, lo_r = 2048 - H/2, i.e. the viewport centre sits in the middle of the 16-bit range and
@@ -324,8 +324,7 @@ constexpr float kRecLimit = 30000.0f;  // |snapped coordinate| (centred) that st
 constexpr unsigned kGuard = 0x10001000u;
 
 struct MvParams {
-    const unsigned *xy;            // [V][Bq]
-    const float *zw;               // [V][Bq]
+    const uint2 *rec;              // [B][V] (xy, z/w bits)
     const int32_t *tri;            // [F,3]
     int F, V, B, Bq;
     int W, H;
@@ -354,8 +353,8 @@ __device__ __forceinline__ void snap_rec(const float4 c, int W, int H, int addx,
     }
 }
 
-__global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int Bq, int W, int H, int addx, int addy, unsigned *xy,
-                                                 float *zw, int *stats, int nstats, VertexPack pack)
+__global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H, int addx, int addy, uint2 *rec,
+                                                 int *stats, int nstats, VertexPack pack)
 {
     wr_pdl_trigger();
     if (blockIdx.x == 0)
@@ -374,33 +373,23 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int Bq, int 
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
     if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
-    uint2 *out_xy = reinterpret_cast<uint2 *>(xy + (size_t)v * Bq);
-    float2 *out_zw = reinterpret_cast<float2 *>(zw + (size_t)v * Bq);
-    for (int b0 = 0; b0 < B; b0 += 2) {
-        unsigned rxy[2];
-        float rzw[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int b = b0 + k;
-            rxy[k] = 0u; rzw[k] = 0.0f;
-            if (b < B) {
-                float4 r0, r1, r2, r3;
-                if (b < kStageViews) {
-                    r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
-                } else {
-                    const float4 *m4 = reinterpret_cast<const float4 *>(src.mvp) + 4 * b;
-                    r0 = __ldg(m4); r1 = __ldg(m4 + 1); r2 = __ldg(m4 + 2); r3 = __ldg(m4 + 3);
-                }
-                float4 c;
-                c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
-                c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
-                c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
-                c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
-                snap_rec(c, W, H, addx, addy, rxy[k], rzw[k]);
-            }
+    for (int b = 0; b < B; ++b) {
+        float4 r0, r1, r2, r3;
+        if (b < kStageViews) {
+            r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
+        } else {
+            const float4 *m4 = reinterpret_cast<const float4 *>(src.mvp) + 4 * b;
+            r0 = __ldg(m4); r1 = __ldg(m4 + 1); r2 = __ldg(m4 + 2); r3 = __ldg(m4 + 3);
         }
-        out_xy[b0 >> 1] = make_uint2(rxy[0], rxy[1]);
-        out_zw[b0 >> 1] = make_float2(rzw[0], rzw[1]);
+        float4 c;
+        c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
+        c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
+        c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
+        c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
+        unsigned rxy;
+        float rzw;
+        snap_rec(c, W, H, addx, addy, rxy, rzw);
+        rec[(size_t)b * src.V + v] = make_uint2(rxy, __float_as_uint(rzw));
     }
 }
 
@@ -418,7 +407,7 @@ __device__ __forceinline__ unsigned mv_box(unsigned a, unsigned c, unsigned d, u
 
 // Sample exactly on an edge or a vertex (m == 0): the top-left rule of DESIGN.md 3.3 on the orientation-normalised
 // edges.  a_i, b_i: vertex i relative to the sample; F_i: orientation-normalised edge functions.
-__device__ __noinline__ bool mv_tie_break(int a0, int b0, int a1, int b1, int a2, int b2, int F0, int F1, int F2,
+__device__ __forceinline__ bool mv_tie_break(int a0, int b0, int a1, int b1, int a2, int b2, int F0, int F1, int F2,
                                           bool flip)
 {
     int dx0 = a2 - a1, dy0 = b2 - b1, dx1 = a0 - a2, dy1 = b0 - b2, dx2 = a1 - a0, dy2 = b1 - b0;
@@ -433,8 +422,8 @@ __device__ __noinline__ bool mv_tie_break(int a0, int b0, int a1, int b1, int a2
 // Depth: the expressions of raster_small; for a clockwise triangle raster_small swaps vertices 1 and 2, which
 // negates the edge functions and lets edges 1 and 2 trade places -- reproduced here by the sign of 1 / area and
 // the selects on `flip` (float negation is exact, and the final + 0.0f removes the sign of a zero).
-__device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, unsigned s0,
-                                          unsigned s1, unsigned s2, int b, int c, int r, uint32_t id)
+__device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, float z0,
+                                          float z1, float z2, int b, int c, int r, uint32_t id)
 {
     const int px = (c + (int)(P.lo_px & 0xFFFFu)) << 4, py = (r + (int)(P.lo_px >> 16)) << 4;
     const int a0 = (int)(xy0 & 0xFFFFu) - px, b0 = (int)(xy0 >> 16) - py;
@@ -448,7 +437,6 @@ __device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsig
     const int m = __vimin3_s32(F0, F1, F2);
     if (m < 0) return;
     if (m == 0 && !mv_tie_break(a0, b0, a1, b1, a2, b2, F0, F1, F2, flip)) return;
-    const float z0 = __ldg(P.zw + (s0 + b)), z1 = __ldg(P.zw + (s1 + b)), z2 = __ldg(P.zw + (s2 + b));
     const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
     const float w0 = __int2float_rn(E0) * inv_area;
     const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
@@ -461,8 +449,8 @@ __device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsig
 
 // One work item whose box holds several samples: classify by size, rasterise a small triangle here (the loop of
 // raster_small with the orientation handled by negating the edge vectors), or report it for the queues.
-__device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, unsigned s0,
-                                         unsigned s1, unsigned s2, int b, uint32_t id, int &push)
+__device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, float z0,
+                                         float z1, float z2, int b, uint32_t id, int &push)
 {
     // signed coordinates relative to the sample of viewport pixel (0, 0)
     const int ox = (int)(P.lo_px & 0xFFFFu) << 4, oy = (int)(P.lo_px >> 16) << 4;
@@ -493,7 +481,6 @@ __device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsign
     const int bias0 = top_left(dx0, dy0) ? 0 : 1;
     const int bias1 = top_left(dx1, dy1) ? 0 : 1;
     const int bias2 = top_left(dx2, dy2) ? 0 : 1;
-    const float z0 = __ldg(P.zw + (s0 + b)), z1 = __ldg(P.zw + (s1 + b)), z2 = __ldg(P.zw + (s2 + b));
     const float za = flip ? z2 : z1, zb = flip ? z1 : z2;
     const float inv_area = 1.0f / __int2float_rn(area2);
     const int px0 = 16 * c0, py0 = 16 * r0;
@@ -541,7 +528,7 @@ __device__ __forceinline__ void mv_push(const MvParams &P, int push, int b, uint
 }
 
 // cold (view, triangle) pair: the contract's own classification from the full snapped vertices
-__device__ __noinline__ void mv_cold(const RasterParams &Pold, const VtxSrc &src, int b, int i0, int i1, int i2, int t,
+__device__ __forceinline__ void mv_cold(const RasterParams &Pold, const VtxSrc &src, int b, int i0, int i1, int i2, int t,
                                      unsigned long long *depth_view, int &push, uint32_t &entry)
 {
     const SnapVert a = snap_one(wr_load_clip(src, b, i0), Pold.W, Pold.H);
@@ -551,61 +538,53 @@ __device__ __noinline__ void mv_cold(const RasterParams &Pold, const VtxSrc &src
 }
 
 #ifndef WR_MV_MINB
-#define WR_MV_MINB 5
+#define WR_MV_MINB 8
 #endif
+// One thread per (view, triangle), blockIdx.y = view: the parallelism of k_setup_triangles with the compact records.
 __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, RasterParams Pold, VtxSrc src,
                                                               const __grid_constant__ FillJob fill)
 {
     wr_pdl_wait();
     wr_pdl_trigger();
-    wr_fill_share(fill, blockIdx.x);
+    wr_fill_share(fill, blockIdx.y * gridDim.x + blockIdx.x);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
     const unsigned lane = threadIdx.x & 31;
-    bool live = t < P.F;
-    int i0 = 0, i1 = 0, i2 = 0;
-    if (live) {
-        i0 = __ldg(P.tri + 3 * (size_t)t); i1 = __ldg(P.tri + 3 * (size_t)t + 1); i2 = __ldg(P.tri + 3 * (size_t)t + 2);
-        live = __vimax3_u32((unsigned)i0, (unsigned)i1, (unsigned)i2) < (unsigned)P.V;
-        if (!live) i0 = i1 = i2 = 0;
-    }
-    // V * Bq < 2^31 (checked by the launcher): 32-bit record indices
-    const unsigned q0 = (unsigned)i0 * (unsigned)P.Bq, q1 = (unsigned)i1 * (unsigned)P.Bq, q2 = (unsigned)i2 * (unsigned)P.Bq;
-    const unsigned lo_px = P.lo_px, hi_px = P.hi_px;
-    const size_t npv = (size_t)P.H * P.W;
-
-    for (int vb = 0; vb < P.B; vb += 2) {
-        uint2 A = make_uint2(0u, 0u), C = A, D = A;
-        if (live) {
-            A = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q0 + vb)));
-            C = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q1 + vb)));
-            D = __ldg(reinterpret_cast<const uint2 *>(P.xy + (q2 + vb)));
-        }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int b = vb + k;
-            if (b >= P.B) break;  // uniform
-            const unsigned a = k ? A.y : A.x, c = k ? C.y : C.x, d = k ? D.y : D.x;
+    int push = 0;
+    uint32_t entry = (uint32_t)t;
+    if (t < P.F) {
+        const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1), i2 = __ldg(P.tri + 3 * (size_t)t + 2);
+        if (__vimax3_u32((unsigned)i0, (unsigned)i1, (unsigned)i2) < (unsigned)P.V) {
+            // B * V < 2^31 (checked by the launcher): 32-bit record indices
+            const unsigned vb = (unsigned)b * (unsigned)P.V;
+            const uint2 ra = __ldg(P.rec + (vb + (unsigned)i0)), rc = __ldg(P.rec + (vb + (unsigned)i1)),
+                        rd = __ldg(P.rec + (vb + (unsigned)i2));
+            const unsigned a = ra.x, c = rc.x, d = rd.x;
             unsigned first;
-            const unsigned tt = mv_box(a, c, d, lo_px, hi_px, first);
+            const unsigned tt = mv_box(a, c, d, P.lo_px, P.hi_px, first);
             // a vertex without a record has xy == 0 (a record's halves are >= 2760)
-            const bool sentinel = __vimin3_u32(a, c, d) == 0u;
-            int push = 0;
-            uint32_t entry = (uint32_t)t;
-            if (live) {
-                if (sentinel) {
-                    mv_cold(Pold, src, b, i0, i1, i2, t, P.depth + (size_t)b * npv, push, entry);
-                } else if ((tt & kGuard) == kGuard) {
-                    if (tt == kGuard) {
-                        const unsigned rel = first - lo_px;  // no borrow: first >= lo_px in both halves
-                        mv_single(P, a, c, d, q0, q1, q2, b, (int)(rel & 0xFFFFu), (int)(rel >> 16), (uint32_t)t);
-                    } else {
-                        mv_multi(P, a, c, d, q0, q1, q2, b, (uint32_t)t, push);
-                    }
+            if (__vimin3_u32(a, c, d) == 0u) {
+                mv_cold(Pold, src, b, i0, i1, i2, t, P.depth + (size_t)b * P.H * P.W, push, entry);
+            } else if ((tt & kGuard) == kGuard) {
+                const float z0 = __uint_as_float(ra.y), z1 = __uint_as_float(rc.y), z2 = __uint_as_float(rd.y);
+                const unsigned rel = first - P.lo_px;  // no borrow: first >= lo_px in both halves
+                const int c0 = (int)(rel & 0xFFFFu), r0 = (int)(rel >> 16);
+                const int nx = (int)(tt & 0xFFFu), ny = (int)((tt >> 16) & 0xFFFu);  // box = (nx + 1) x (ny + 1) samples
+                if ((nx + 1) * (ny + 1) <= 4) {
+                    // up to four samples (a box of four samples spans less than five pixels: exact in int32): the
+                    // single-sample evaluation per sample; lanes with fewer samples idle for a few instructions
+                    // instead of everybody paying the edge set-up and loop of mv_multi
+#pragma unroll 1
+                    for (int r = r0; r <= r0 + ny; ++r)
+#pragma unroll 1
+                        for (int cc = c0; cc <= c0 + nx; ++cc) mv_single(P, a, c, d, z0, z1, z2, b, cc, r, (uint32_t)t);
+                } else {
+                    mv_multi(P, a, c, d, z0, z1, z2, b, (uint32_t)t, push);
                 }
             }
-            mv_push(P, push, b, entry, lane);
         }
     }
+    mv_push(P, push, b, entry, lane);
 }
 
 // One warp rasterises one snapped triangle (or the stripe-th share of its 16x16 blocks).
@@ -897,8 +876,8 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
 #endif
     const int Bp = (B + 1) & ~1;
     const bool use_mv = WR_MV && src.mvp && !tri_ranges && W <= 2048 && H <= 2048 && F > 0 && V > 0 &&
-                        (long long)F * 4 > (long long)H * W && (long long)V * Bp < (1ll << 31);
-    const size_t sv_bytes = use_mv ? wr_align256((size_t)V * Bp * sizeof(int2))
+                        (long long)F * 4 > (long long)H * W && (long long)V * B < (1ll << 31);
+    const size_t sv_bytes = use_mv ? wr_align256((size_t)V * B * sizeof(int2))
                                    : wr_align256((size_t)B * (size_t)(V > 0 ? V : 1) * sizeof(SnapVert));
     const size_t depth_bytes = wr_align256((size_t)B * H * W * sizeof(unsigned long long));
     const size_t queue_bytes = wr_align256((size_t)B * (size_t)(F > 0 ? F : 1) * sizeof(uint32_t));
@@ -953,9 +932,8 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
         wr_stage(ctx, stream, "k_snap_vertices");
         if (use_mv) {
             MvParams M;
-            unsigned *rec_xy = reinterpret_cast<unsigned *>(sv);
-            float *rec_zw = reinterpret_cast<float *>(rec_xy + (size_t)V * Bp);
-            M.xy = rec_xy; M.zw = rec_zw; M.tri = tri; M.F = F; M.V = V; M.B = B; M.Bq = Bp;
+            uint2 *rec = reinterpret_cast<uint2 *>(sv);
+            M.rec = rec; M.tri = tri; M.F = F; M.V = V; M.B = B; M.Bq = B;
             M.W = W; M.H = H;
             const int lo_c = 2048 - W / 2, lo_r = 2048 - H / 2;
             M.lo_px = (unsigned)lo_c | ((unsigned)lo_r << 16);
@@ -964,12 +942,12 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
             P.sv = nullptr;  // the queue pass recomputes the few snapped vertices it needs
             // stored = snapped (centred) + 8 W - 8 (relative to the sample of pixel 0) + 16 lo_c (bias)
             k_snap_mv<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
-                src, B, Bp, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec_xy, rec_zw, stats, B * 8, vp);
+                src, B, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec, stats, B * 8, vp);
             WR_CHECK_LAUNCH(ctx, "k_snap_mv");
             wr_stage(ctx, stream, "k_setup_triangles");
             const bool pdl = !ctx->profiling;
-            wr_fill_plan(&FJ, (unsigned)wr_div_up(F, 256));
-            wr_launch(k_setup_mv, dim3(wr_div_up(F, 256)), dim3(256), stream, pdl, M, P, src, FJ);
+            wr_fill_plan(&FJ, (unsigned)(wr_div_up(F, 256) * B));
+            wr_launch(k_setup_mv, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, M, P, src, FJ);
             WR_CHECK_LAUNCH(ctx, "k_setup_mv");
             wr_stage(ctx, stream, "k_raster_queues");
             wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);

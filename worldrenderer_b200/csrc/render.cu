@@ -37,6 +37,7 @@ struct ShadeParams {
     int wide_ok;                 // W % 4 == 0 and 16-byte aligned pos / normal maps: background rows may use 16-byte stores
     int bg_final;                // two-pass depth whose background value is a constant (controlnet, zero123++):
                                  // written here, k_depth_finalize then only touches covered pixels
+    unsigned perm_mul;           // multiplier of the block permutation (0 = identity)
 };
 
 struct PixelGeo {
@@ -248,9 +249,24 @@ __global__ void __launch_bounds__(WR_SHADE_THREADS, WR_SHADE_MINB) k_shade(Shade
 
     wr_pdl_wait();
     wr_pdl_trigger();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r0 = blockIdx.y * kShadeRows;
-    const int b = blockIdx.z;
+    // Block -> strip assignment.  Blocks are dispatched in index order, so with the identity map the blocks resident
+    // at any moment are neighbours in one view: all background (bound by their stores) or all covered (bound by the
+    // latency of their dependent gathers), one phase after the other.  A multiplicative permutation of the linear
+    // block index (P.perm_mul is coprime to the block count) makes the resident set a sample of the whole job, so
+    // that the store-bound and the latency-bound blocks overlap.
+    unsigned bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    if (P.perm_mul) {
+        const unsigned n = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned lin = bx + gridDim.x * (by + gridDim.y * bz);
+        const unsigned q = (unsigned)(((unsigned long long)lin * P.perm_mul) % n);
+        bx = q % gridDim.x;
+        const unsigned t2 = q / gridDim.x;
+        by = t2 % gridDim.y;
+        bz = t2 / gridDim.y;
+    }
+    const int c = bx * blockDim.x + threadIdx.x;
+    const int r0 = by * kShadeRows;
+    const int b = bz;
     const int W = A.W, H = A.H;
     const bool live = c < W;
 
@@ -524,7 +540,7 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     FillJob fill;
     fill.nseg = 0; fill.total16 = 0; fill.stride = 1; fill.shares = 1;
 #ifndef WR_PREFILL
-#define WR_PREFILL 1
+#define WR_PREFILL 0
 #endif
     {
         const bool extras0 = A.out_tri_id || A.out_rast || A.out_attr || A.out_tangent;
@@ -582,6 +598,20 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     wr_stage(ctx, stream, "k_shade");
     {
         const dim3 grid(wr_div_up(A.W, WR_SHADE_THREADS), wr_div_up(A.H, kShadeRows), A.B);
+#ifndef WR_SHADE_PERM
+#define WR_SHADE_PERM 0
+#endif
+        P.perm_mul = 0;
+        if (WR_SHADE_PERM) {
+            const unsigned long long n = (unsigned long long)grid.x * grid.y * grid.z;
+            if (n > 64 && n < (1ull << 31)) {
+                // a multiplier near n / golden ratio, made coprime to n
+                unsigned long long m = (unsigned long long)((double)n * 0.6180339887498949) | 1ull;
+                auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { const unsigned long long t = a % b; a = b; b = t; } return a; };
+                while (gcd(m, n) != 1) m += 2;
+                P.perm_mul = (unsigned)(m % n);
+            }
+        }
         const bool extras = A.out_tri_id || A.out_rast || A.out_attr || A.out_tangent;
         const bool plain = P.mask && A.out_pos && A.out_normal && A.out_depth && !A.out_geo && !extras;
         const bool bake = P.mask && A.out_geo && A.out_depth && !two_pass && !A.out_pos && !A.out_normal && !extras;
