@@ -22,11 +22,12 @@ def _same(a, b):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
 
 
-def test_graph_replay_equals_eager(wr_ctx):
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_graph_replay_equals_eager(wr_ctx, lanes):
     dev = wr_ctx.device
     cam = cases.canonical_cameras(device=dev)
     meshes = [_mesh(*cases.terrain_mesh(96, 64, seed=s), dev) for s in range(3)] + [_mesh(*cases.icosphere_mesh(8), dev)]
-    g = wr.RenderGraph(wr_ctx, [(m, cam) for m in meshes], 64, 64, render_attr=False)
+    g = wr.RenderGraph(wr_ctx, [(m, cam) for m in meshes], 64, 64, lanes=lanes, render_attr=False)
     for _ in range(3):   # replays are idempotent (the packed buffer cleans itself)
         outs = g.replay()
     torch.cuda.synchronize()

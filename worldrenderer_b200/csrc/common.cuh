@@ -156,7 +156,8 @@ static inline void wr_fill_plan(FillJob *J, unsigned nblocks)
 #ifdef __CUDACC__
 __device__ __forceinline__ void wr_fill_share(const FillJob &J, unsigned bid)
 {
-    if (J.nseg == 0 || bid % J.stride != 0) return;
+    if (J.nseg == 0) return;
+    if (bid % J.stride != 0) return;
     const unsigned share = bid / J.stride;
 #pragma unroll 1
     for (int s = 0; s < J.nseg; ++s) {

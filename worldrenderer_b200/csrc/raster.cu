@@ -311,15 +311,13 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
 // recomputes the full 16-byte snapped vertices from the source and runs setup_one (the contract's one and only
 // statement of culling / clipping) -- so the compact records can never change a result.
 //
-// k_setup_mv: one thread per TRIANGLE.  The three indices are read once for all views; per pair of views three
-// 8-byte loads fetch the xy words; packed 16-bit min3 / max3 and a handful of SIMD-in-a-word operations decide
-// whether the bounding box holds a sample at all -- most (view, triangle) pairs of a dense mesh end there
-// (~16 instructions instead of ~80 in the per-view kernel).  The pairs that do hold a sample become work items in
-// a per-warp list in shared memory (ballot-compacted, ordered by view and lane) and are then evaluated by ALL
-// lanes of the warp, one item per lane and round, so the lanes of a round are full no matter how few triangles of
-// a view had a sample.  Items whose box holds exactly one sample (the common case for sub-pixel triangles) are
-// evaluated by three integer cross products around that sample; the others walk their box like raster_small.
-constexpr int kMvChunk = 8;            // views classified per compaction round
+// k_setup_mv: one thread per (view, triangle).  One 8-byte load per vertex fetches xy and z/w; packed 16-bit
+// min3 / max3 and a handful of SIMD-in-a-word operations decide whether the bounding box holds a sample at all --
+// half of the (view, triangle) pairs of a dense mesh end there (~16 instructions instead of ~80 in the per-view
+// kernel).  A triangle that spans less than two pixels (at most 2 x 2 samples) is tested sample by sample with
+// three cross products of PERTURBED coordinates that carry the top-left rule (mv_fast), slivers of up to four
+// samples with the plain cross products and an explicit tie-break (mv_single); everything else walks its box like
+// raster_small or goes to the queues.
 constexpr float kRecLimit = 30000.0f;  // |snapped coordinate| (centred) that still gets a record
 constexpr unsigned kGuard = 0x10001000u;
 
@@ -447,6 +445,48 @@ __device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsig
         resolve_sample(P.depth + ((size_t)b * P.H * P.W + (unsigned)(r * P.W + c)), zw, id);
 }
 
+// Sample (pc, pr) (biased pixel coordinates) of a triangle that spans less than two pixels in x and in y, so that
+// the vertices relative to the sample satisfy |a_i|, |b_i| <= 31.  Coverage including the top-left rule comes from
+// ONE set of cross products: with a_i' = 1024 a_i - 32, b_i' = 1024 b_i - 1 (the sample moved by (1/32, 1/1024) of
+// a sub-pixel unit towards +x, +y)
+//     E0' = a1' b2' - a2' b1' = 2^20 E0 + 1024 (dx0 - 32 dy0),      (dx0, dy0) = v2 - v1, |dx0 - 32 dy0| <= 1023,
+// so E0' has the sign of E0 when E0 != 0 and otherwise the sign of (dx0 - 32 dy0), which is positive exactly for
+// a left edge (dy0 < 0) or a top edge (dy0 == 0, dx0 > 0) of a counter-clockwise triangle; for a clockwise one
+// every sign flips, E' included.  Hence: covered <=> E0', E1', E2' all > 0 or all < 0 (their sum is 2^20 * area2,
+// so a zero-area triangle can never pass).  |a_i'|, |b_i'| < 2^15: the products fit int32.  Equivalent to the
+// orientation-normalised `e >= bias` test of raster_small bit for bit; the depth expressions are mv_single's.
+__device__ __forceinline__ void mv_fast(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, float z0, float z1,
+                                        float z2, unsigned long long *depth_view, unsigned pxy, uint32_t id)
+{
+    const int pc = (int)(pxy & 0xFFFFu), pr = (int)(pxy >> 16);
+    const int cx = (pc << 14) + 32, cy = (pr << 14) + 1;   // 1024 * 16 * pixel + offset
+    const int x0 = (int)(xy0 & 0xFFFFu), y0 = (int)(xy0 >> 16);
+    const int x1 = (int)(xy1 & 0xFFFFu), y1 = (int)(xy1 >> 16);
+    const int x2 = (int)(xy2 & 0xFFFFu), y2 = (int)(xy2 >> 16);
+    const int a0 = x0 * 1024 - cx, b0 = y0 * 1024 - cy;
+    const int a1 = x1 * 1024 - cx, b1 = y1 * 1024 - cy;
+    const int a2 = x2 * 1024 - cx, b2 = y2 * 1024 - cy;
+    const int Q0 = a1 * b2 - a2 * b1, Q1 = a2 * b0 - a0 * b2, Q2 = a0 * b1 - a1 * b0;
+    const int lo = __vimin3_s32(Q0, Q1, Q2), hi = __vimax3_s32(Q0, Q1, Q2);
+    if (lo <= 0 && hi >= 0) return;
+    // covered: the exact edge functions for the depth (E_i = (Q_i - 1024 (dx_i - 32 dy_i)) / 2^20)
+    const int px = pc << 4, py = pr << 4;
+    const int u0 = x0 - px, v0 = y0 - py, u1 = x1 - px, v1 = y1 - py, u2 = x2 - px, v2 = y2 - py;
+    const int E0 = u1 * v2 - u2 * v1, E1 = u2 * v0 - u0 * v2, E2 = u0 * v1 - u1 * v0;
+    const int area2 = E0 + E1 + E2;
+    const bool flip = lo < 0;
+    const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
+    const float w0 = __int2float_rn(E0) * inv_area;
+    const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
+    const float w2 = (1.0f - w0) - w1;
+    float zw = ((z0 * w0) + ((flip ? z2 : z1) * w1)) + ((flip ? z1 : z2) * w2);
+    zw = zw + 0.0f;
+    if (zw >= -1.0f && zw <= 1.0f) {
+        const unsigned rel = pxy - P.lo_px;  // no borrow: the sample lies in the viewport
+        resolve_sample(depth_view + ((rel >> 16) * (unsigned)P.W + (rel & 0xFFFFu)), zw, id);
+    }
+}
+
 // One work item whose box holds several samples: classify by size, rasterise a small triangle here (the loop of
 // raster_small with the orientation handled by negating the edge vectors), or report it for the queues.
 __device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, float z0,
@@ -567,19 +607,36 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
                 mv_cold(Pold, src, b, i0, i1, i2, t, P.depth + (size_t)b * P.H * P.W, push, entry);
             } else if ((tt & kGuard) == kGuard) {
                 const float z0 = __uint_as_float(ra.y), z1 = __uint_as_float(rc.y), z2 = __uint_as_float(rd.y);
-                const unsigned rel = first - P.lo_px;  // no borrow: first >= lo_px in both halves
-                const int c0 = (int)(rel & 0xFFFFu), r0 = (int)(rel >> 16);
-                const int nx = (int)(tt & 0xFFFu), ny = (int)((tt >> 16) & 0xFFFu);  // box = (nx + 1) x (ny + 1) samples
-                if ((nx + 1) * (ny + 1) <= 4) {
-                    // up to four samples (a box of four samples spans less than five pixels: exact in int32): the
-                    // single-sample evaluation per sample; lanes with fewer samples idle for a few instructions
-                    // instead of everybody paying the edge set-up and loop of mv_multi
+                unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
+                const unsigned mn = __vimin3_u16x2(a, c, d), mx = __vimax3_u16x2(a, c, d);
+                if (((mx - mn) & 0xFFE0FFE0u) == 0u) {
+                    // spans less than two pixels: 1, 2 or 2 x 2 samples
+                    mv_fast(P, a, c, d, z0, z1, z2, depth_view, first, (uint32_t)t);
+                    if (tt != kGuard) {
+                        // second column (bit 0), second row (bit 1), both (bit 2)
+                        const unsigned ex = tt & 1u, ey = (tt >> 16) & 1u;
+                        unsigned pending = ex | (ey << 1) | ((ex & ey) << 2);
 #pragma unroll 1
-                    for (int r = r0; r <= r0 + ny; ++r)
-#pragma unroll 1
-                        for (int cc = c0; cc <= c0 + nx; ++cc) mv_single(P, a, c, d, z0, z1, z2, b, cc, r, (uint32_t)t);
+                        while (pending) {
+                            const unsigned j = __ffs(pending) - 1u;
+                            pending &= pending - 1u;
+                            mv_fast(P, a, c, d, z0, z1, z2, depth_view, first + (j == 0u ? 1u : (j == 1u ? 0x10000u : 0x10001u)),
+                                    (uint32_t)t);
+                        }
+                    }
                 } else {
-                    mv_multi(P, a, c, d, z0, z1, z2, b, (uint32_t)t, push);
+                    const unsigned rel = first - P.lo_px;  // no borrow: first >= lo_px in both halves
+                    const int c0 = (int)(rel & 0xFFFFu), r0 = (int)(rel >> 16);
+                    const int nx = (int)(tt & 0xFFFu), ny = (int)((tt >> 16) & 0xFFFu);  // box = (nx + 1) x (ny + 1) samples
+                    if ((nx + 1) * (ny + 1) <= 4 && ((mx - mn) & 0xFF80FF80u) == 0u) {
+                        // a sliver of up to four samples that spans less than eight pixels (exact in int32)
+#pragma unroll 1
+                        for (int r = r0; r <= r0 + ny; ++r)
+#pragma unroll 1
+                            for (int cc = c0; cc <= c0 + nx; ++cc) mv_single(P, a, c, d, z0, z1, z2, b, cc, r, (uint32_t)t);
+                    } else {
+                        mv_multi(P, a, c, d, z0, z1, z2, b, (uint32_t)t, push);
+                    }
                 }
             }
         }

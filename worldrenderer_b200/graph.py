@@ -6,6 +6,10 @@ the GPU and the gaps land inside the step.  `RenderGraph` captures the render() 
 config D is eight meshes per GPU per step -- into ONE CUDA graph (the kernels keep their programmatic
 dependent launch edges), so that a step is a single `cudaGraphLaunch`.
 
+`lanes > 1` captures the jobs round-robin on that many streams, each with a raster context (scratch) of its own,
+so the graph holds independent chains: the raster set-up of one mesh is bound by instruction issue, the shading
+pass of another by the latency of its gathers and by its stores, and the two overlap when they run side by side.
+
 The output tensors are static: every replay overwrites them.  Vertex positions, faces and cameras are read
 from the tensors the job list held at capture time -- update those in place (copy_) to render new data of the
 same shape.
@@ -23,31 +27,55 @@ from .render import NVDiffRastContextWrapper, RenderOutput, render
 
 class RenderGraph:
     def __init__(self, ctx: NVDiffRastContextWrapper, jobs: Sequence[Tuple[TexturedMesh, Camera]], height: int,
-                 width: int, warmup: int = 2, **render_kwargs):
+                 width: int, warmup: int = 2, lanes: int = 1, **render_kwargs):
         if not jobs:
             raise ValueError("RenderGraph needs at least one (mesh, camera) job")
-        # a context of its own: the captured kernels hold pointers into the context's scratch, which an eager call
-        # of a larger shape on a shared context would reallocate
-        self.ctx = NVDiffRastContextWrapper(str(ctx.device), ctx.context_type)
-        ctx = self.ctx
         self.jobs, self.height, self.width = list(jobs), int(height), int(width)
         self.kwargs = dict(render_kwargs)
+        self.lanes = max(1, min(int(lanes), len(self.jobs)))
+        # contexts of its own: the captured kernels hold pointers into a context's scratch, which an eager call
+        # of a larger shape on a shared context would reallocate; one per lane, because concurrent chains cannot
+        # share the packed visibility buffer
+        self.ctxs = [NVDiffRastContextWrapper(str(ctx.device), ctx.context_type) for _ in range(self.lanes)]
+        self.ctx = self.ctxs[0]
+        dev = self.ctx.device
         for mesh, _ in self.jobs:
             if self.kwargs.get("render_normal", True):
                 mesh.v_nrm  # lazily computed once, outside the capture
-        side = torch.cuda.Stream(ctx.device)
-        side.wait_stream(torch.cuda.current_stream(ctx.device))
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):   # scratch growth (cudaMalloc) and index caches happen here
-                self._run()
-        torch.cuda.current_stream(ctx.device).wait_stream(side)
-        torch.cuda.synchronize(ctx.device)
+                self._run_serial()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._lane_streams = [torch.cuda.Stream(dev) for _ in range(self.lanes - 1)]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.outputs: List[RenderOutput] = self._run()
+            self.outputs: List[RenderOutput] = self._run_lanes()
 
-    def _run(self) -> List[RenderOutput]:
-        return [render(self.ctx, m, c, self.height, self.width, **self.kwargs) for m, c in self.jobs]
+    def _render(self, lane: int, job: int) -> RenderOutput:
+        m, c = self.jobs[job]
+        return render(self.ctxs[lane], m, c, self.height, self.width, **self.kwargs)
+
+    def _run_serial(self) -> List[RenderOutput]:
+        return [self._render(j % self.lanes, j) for j in range(len(self.jobs))]
+
+    def _run_lanes(self) -> List[RenderOutput]:
+        if self.lanes == 1:
+            return self._run_serial()
+        main = torch.cuda.current_stream(self.ctx.device)
+        outs: List[RenderOutput] = [None] * len(self.jobs)  # type: ignore[list-item]
+        for s in self._lane_streams:       # fork
+            s.wait_stream(main)
+        for lane in range(self.lanes):
+            stream = main if lane == 0 else self._lane_streams[lane - 1]
+            with torch.cuda.stream(stream):
+                for j in range(lane, len(self.jobs), self.lanes):
+                    outs[j] = self._render(lane, j)
+        for s in self._lane_streams:       # join
+            main.wait_stream(s)
+        return outs
 
     def replay(self) -> List[RenderOutput]:
         self.graph.replay()
