@@ -15,6 +15,9 @@
  *   wr_interpolate                   dr.interpolate    render.py:64-81  (render.py:244,261,275,281; uv.py:43)
  *   wr_texture                       dr.texture        render.py:83-120 (render.py:267)
  *   wr_vertex_normals                TexturedMesh._compute_vertex_normal            mesh.py:85-119
+ *   wr_vertex_tangents               TexturedMesh._compute_tangent                  mesh.py:121-167
+ *   wr_tangent_space_normals         view normal maps -> UV tangent space, the inline block of
+ *                                    mvadapter/test/utils/pipeline_texture.py:358-396
  *   wr_render                        render() fused: clip transform utils.py:127-129, rasterize,
  *                                    interpolate pos/normal/uv, view depth utils.py:132-139,
  *                                    background fill + depth normalisers render.py:164-217,247-258,
@@ -95,6 +98,17 @@ int wr_texture(wr_ctx *ctx, const float *tex, int tex_B, int TH, int TW, int C, 
 /* mesh.py:85-119.  v_nrm: [V,3] out (used as the accumulator; float atomics => sum order varies). */
 int wr_vertex_normals(wr_ctx *ctx, const float *v_pos, int V, const int32_t *tri, int F, float *v_nrm,
                       void *stream);
+
+/* mesh.py:121-167.  tri / tri_tex: [F,3] position and UV faces; v_nrm: [V,3] in; v_tang: [V,3] out.  The per-vertex
+ * sum runs through float atomics (sum order varies); a vertex without a face gets NaN, as in the reference. */
+int wr_vertex_tangents(wr_ctx *ctx, const float *v_pos, int V, const int32_t *tri, const float *v_tex, int Vt,
+                       const int32_t *tri_tex, int F, const float *v_nrm, float *v_tang, void *stream);
+
+/* pipeline_texture.py:358-396.  normal, tangent: [B,H,W,3] rendered maps (render(..., render_tangent=True));
+ * image: [B,H,W,3] the views' normal images in [0,1]; view_axis: [B,3] the geometry tangent axis of each view;
+ * out: [B,H,W,3] tangent-space normal colours in [0,1]. */
+int wr_tangent_space_normals(wr_ctx *ctx, const float *normal, const float *tangent, const float *image,
+                             const float *view_axis, int B, int H, int W, float *out, void *stream);
 
 /* depth normalisers of render.py:164-217 */
 enum { WR_DEPTH_NONE = 0, WR_DEPTH_CONTROLNET = 1, WR_DEPTH_ZERO123PP = 2, WR_DEPTH_SIMPLE = 3 };

@@ -175,6 +175,85 @@ def bake_cases(mu):
     np.savez_compressed(os.path.join(OUT, "bake_sphere.npz"), **out)
 
 
+def operator_cases(mu):
+    """The dr.* operator boundary itself: the clip-space positions the REFERENCE hands to dr.rasterize (its own
+    torch.matmul, utils.py:127-129, and its own UV -> clip construction, uv.py:28-38) are recorded together with
+    what came back, so that the GPU operators can be checked bit for bit on exactly those inputs -- no restated
+    clip transform in between."""
+    dr = sys.modules["nvdiffrast.torch"]
+    rec = {"rasterize": [], "interpolate": []}
+    orig_r, orig_i = dr.rasterize, dr.interpolate
+
+    def rasterize(ctx, pos, tri, resolution, *a, **kw):
+        out = orig_r(ctx, pos, tri, resolution, *a, **kw)
+        rec["rasterize"].append((_np(pos).copy(), _np(tri).copy(), tuple(int(x) for x in resolution), _np(out[0]).copy()))
+        return out
+
+    def interpolate(attr, rast, tri, *a, **kw):
+        out = orig_i(attr, rast, tri, *a, **kw)
+        rec["interpolate"].append((_np(attr).copy(), _np(rast).copy(), _np(tri).copy(), _np(out[0]).copy()))
+        return out
+
+    dr.rasterize, dr.interpolate = rasterize, interpolate
+    try:
+        ctx = mu.NVDiffRastContextWrapper("cpu", "cuda")
+        m = _sphere_mesh(mu, 6, 16)
+        mu.render(ctx, m, mu.get_orthogonal_camera(**synth.CANONICAL_RIG), 64, 64, render_attr=True)
+        t = _terrain_mesh(mu, 32, 16)
+        mu.render(ctx, t, mu.get_camera(elevation_deg=[10.0, -20.0, 35.0, 60.0], distance=[1.8] * 4, fovy_deg=[40.0] * 4,
+                                        azimuth_deg=[0.0, 75.0, 160.0, 250.0], aspect_wh=64 / 48), 48, 64, render_attr=False)
+        mu.render(ctx, t, mu.get_camera(elevation_deg=[5.0, 40.0], distance=[0.3, 0.45], fovy_deg=[70.0, 90.0],
+                                        azimuth_deg=[20.0, 200.0], near=0.05, far=10.0, aspect_wh=64 / 48), 48, 64,
+                  render_attr=False)
+        mu.uv.uv_precompute(ctx, m, 64, 64)
+    finally:
+        dr.rasterize, dr.interpolate = orig_r, orig_i
+    out = {"n_rasterize": len(rec["rasterize"]), "n_interpolate": len(rec["interpolate"])}
+    for k, (pos, tri, res, rast) in enumerate(rec["rasterize"]):
+        out.update({f"r{k}_pos": pos, f"r{k}_tri": tri.astype(np.int32), f"r{k}_res": np.asarray(res), f"r{k}_rast": rast})
+    for k, (attr, rast, tri, val) in enumerate(rec["interpolate"]):
+        out.update({f"i{k}_attr": attr, f"i{k}_rast": rast, f"i{k}_tri": tri.astype(np.int32), f"i{k}_out": val})
+    np.savez_compressed(os.path.join(OUT, "operators.npz"), **out)
+    print("operators:", out["n_rasterize"], "rasterize calls,", out["n_interpolate"], "interpolate calls")
+
+
+def _reference_block(path, first, last):
+    """Source lines of the reference from the line containing `first` to the one containing `last` (inclusive),
+    dedented -- executed, never stored: the tangent-space bake of pipeline_texture.py is inline code of a method."""
+    import textwrap
+    lines = open(path).read().splitlines()
+    a = next(i for i, l in enumerate(lines) if first in l)
+    b = next(i for i, l in enumerate(lines) if last in l and i > a)
+    return textwrap.dedent("\n".join(lines[a:b + 1]))
+
+
+def tangent_cases(mu):
+    """TexturedMesh.v_tang (mesh.py:121-167), render(render_tangent=True) (render.py:280-284) and the tangent-space
+    rotation of the normal modality (mvadapter/test/utils/pipeline_texture.py:358-398), all run by the reference."""
+    import types
+    import torch.nn.functional as F
+    ctx = mu.NVDiffRastContextWrapper("cpu", "cuda")
+    m = _sphere_mesh(mu, 6, 16)
+    cam = mu.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    out = _mesh_inputs(m)
+    out.update(mvp=_np(cam.mvp_mtx), w2c=_np(cam.w2c), v_nrm=_np(m.v_nrm), v_tang=_np(m.v_tang))
+    render_out = mu.render(ctx, m, cam, 64, 64, render_attr=False, render_depth=False, render_normal=True,
+                           render_tangent=True)
+    out.update(normal=_np(render_out.normal), tangent=_np(render_out.tangent), mask=_np(render_out.mask))
+    rng = np.random.default_rng(11)
+    nimg = rng.normal(0, 1, (6, 64, 64, 3))
+    nimg[..., 2] = np.abs(nimg[..., 2]) + 0.5
+    nimg = (nimg / np.linalg.norm(nimg, axis=-1, keepdims=True) * 0.5 + 0.5).astype(np.float32)
+    out["normal_images"] = nimg
+    src = _reference_block(os.path.join(ref_shim.REFERENCE_ROOT, "mvadapter", "test", "utils", "pipeline_texture.py"),
+                           "# compute UV tangent space", "mod_tensor = (mod_tensor * 0.5 + 0.5).clamp(0, 1)")
+    ns = {"torch": torch, "F": F, "render_out": render_out, "mod_tensor": torch.from_numpy(nimg),
+          "self": types.SimpleNamespace(device="cpu")}
+    exec(src, ns)
+    out["tangent_space"] = _np(ns["mod_tensor"])
+    np.savez_compressed(os.path.join(OUT, "tangent.npz"), **out)
+
+
 def poisson_cases(mu):
     """The reference's own PoissonBlendingSolver (blend.py:186-324) on CPU, "torch-native" backend, unmodified;
     then its uv_blend / CameraProjection with Poisson blending + padding, where only cvcuda.inpaint is served by the
@@ -293,6 +372,8 @@ def main():
     bake_cases(mu)
     poisson_cases(mu)
     smart_paint_case(mu)
+    operator_cases(mu)
+    tangent_cases(mu)
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
 

@@ -50,6 +50,57 @@ def vertex_normals(v_pos, tri) -> np.ndarray:
     return (acc / np.maximum(n, f32(1e-12))).astype(f32)  # F.normalize, eps 1e-12
 
 
+def _normalize_rows(x: np.ndarray) -> np.ndarray:
+    """F.normalize(x, dim=-1): x / max(|x|, 1e-12), the squares summed left to right."""
+    n = np.sqrt((x[..., 0] * x[..., 0] + x[..., 1] * x[..., 1]) + x[..., 2] * x[..., 2]).astype(f32)
+    return (x / np.maximum(n, f32(1e-12))[..., None]).astype(f32)
+
+
+def vertex_tangents(v_pos, tri, v_tex, tri_tex, v_nrm) -> np.ndarray:
+    """mesh.py:121-167: per-face tangent from the UV gradients, mean over the faces of a vertex, normalised, made
+    perpendicular to the vertex normal, normalised again.  A vertex without a face is 0 / 0 = NaN (as there)."""
+    v, vt, n = _a(v_pos), _a(v_tex), _a(v_nrm)
+    t = np.asarray(tri, np.int64).reshape(-1, 3)
+    tt = np.asarray(tri_tex, np.int64).reshape(-1, 3)
+    uve1, uve2 = vt[tt[:, 1]] - vt[tt[:, 0]], vt[tt[:, 2]] - vt[tt[:, 0]]                     # mesh.py:135-136
+    pe1, pe2 = v[t[:, 1]] - v[t[:, 0]], v[t[:, 2]] - v[t[:, 0]]                               # mesh.py:137-138
+    nom = (pe1 * uve2[:, 1:2] - pe2 * uve1[:, 1:2]).astype(f32)                               # mesh.py:140
+    den = (uve1[:, 0:1] * uve2[:, 1:2] - uve1[:, 1:2] * uve2[:, 0:1]).astype(f32)             # mesh.py:141
+    with np.errstate(all="ignore"):
+        den = np.where(den > 0, np.maximum(den, f32(1e-6)), np.minimum(den, f32(-1e-6))).astype(f32)  # mesh.py:144-146
+        tang = (nom / den).astype(f32)
+        acc = np.zeros_like(n)
+        cnt = np.zeros_like(n)
+        for k in range(3):                                                                     # mesh.py:149-155
+            np.add.at(acc, t[:, k], tang)
+            np.add.at(cnt, t[:, k], f32(1))
+        out = _normalize_rows((acc / cnt).astype(f32))                                        # mesh.py:156-159
+        d = ((out[:, 0] * n[:, 0] + out[:, 1] * n[:, 1]) + out[:, 2] * n[:, 2]).astype(f32)
+        return _normalize_rows((out - d[:, None] * n).astype(f32))                            # mesh.py:160-162
+
+
+def _cross(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                     a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], -1).astype(f32)
+
+
+def tangent_space_normals(normal, tangent, image, view_axis) -> np.ndarray:
+    """mvadapter/test/utils/pipeline_texture.py:358-396: view normal images [B,H,W,3] in [0,1] (geometry tangent frame
+    of each view) -> colours of the same normals in the UV tangent frame (rendered tangent, bitangent, normal)."""
+    vN, vT, img = _a(normal), _a(tangent), _a(image)
+    g = np.broadcast_to(_a(view_axis)[:, None, None, :], vN.shape)
+    T, B_, N = _normalize_rows(vT), _normalize_rows(_cross(vN, vT)), _normalize_rows(vN)      # :359-362
+    gb = _cross(vN, g)                                                                         # :365-382
+    gt = _cross(gb, vN)
+    GT, GB = _normalize_rows(gt), _normalize_rows(gb)                                          # :383-385
+    m = (img * f32(2) - f32(1)).astype(f32)                                                    # :388
+    world = _normalize_rows(((m[..., 0:1] * GT + m[..., 1:2] * GB) + m[..., 2:3] * N).astype(f32))  # :389-395
+    rows = [((world[..., 0] * F_[..., 0] + world[..., 1] * F_[..., 1]) + world[..., 2] * F_[..., 2]).astype(f32)
+            for F_ in (T, B_, N)]
+    out = _normalize_rows(np.stack(rows, -1))                                                  # :398-400
+    return np.clip(out * f32(0.5) + f32(0.5), f32(0), f32(1)).astype(f32)                     # :401
+
+
 # ---------------------------------------------------------------------------------------------
 # render.py:164-217  depth normalisation strategies (specs are plain tuples here)
 # ---------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ _LIB: Optional[ctypes.CDLL] = None
 SYMBOLS = [
     "wr_status_string", "wr_ctx_last_error", "wr_version", "wr_ctx_create", "wr_ctx_destroy",
     "wr_ctx_scratch_bytes", "wr_ctx_profile", "wr_ctx_profile_read", "wr_ctx_profile_stage_name", "wr_rasterize", "wr_interpolate", "wr_texture", "wr_vertex_normals",
+    "wr_vertex_tangents", "wr_tangent_space_normals",
     "wr_render", "wr_view_prep", "wr_uv_unproject", "wr_uv_finalize", "wr_grid_sample", "wr_uv_reduce_finalize_p2p",
     "wr_poisson_blend", "wr_inpaint_u8", "wr_uv_padding", "wr_view_scores",
 ]
@@ -115,6 +116,10 @@ def lib() -> ctypes.CDLL:
     L.wr_texture.argtypes = [vp, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp]
     L.wr_vertex_normals.restype = ci
     L.wr_vertex_normals.argtypes = [vp, vp, ci, vp, ci, vp, vp]
+    L.wr_vertex_tangents.restype = ci
+    L.wr_vertex_tangents.argtypes = [vp, vp, ci, vp, vp, ci, vp, ci, vp, vp, vp]
+    L.wr_tangent_space_normals.restype = ci
+    L.wr_tangent_space_normals.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]
     L.wr_render.restype = ci
     L.wr_render.argtypes = [vp, ctypes.POINTER(RenderArgs), vp]
     L.wr_view_prep.restype = ci

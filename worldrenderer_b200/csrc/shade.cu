@@ -89,6 +89,105 @@ __global__ void __launch_bounds__(256) k_normalize_vertex_normals(float *acc, in
     acc[3 * (size_t)v] = x / d; acc[3 * (size_t)v + 1] = y / d; acc[3 * (size_t)v + 2] = z / d;
 }
 
+// ------------------------------------------------------------------------------------------
+// vertex tangents (mesh.py:121-167): per-face tangent from the UV gradients, averaged over the faces of a
+// vertex, normalised, made perpendicular to the vertex normal, normalised again.
+// acc [V,4]: (sum of face tangents, face count).  Operation order of every expression: oracle/render_oracle.py
+// vertex_tangents (only the order of the per-vertex sum is free, as for the normals).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_face_tangents_scatter(const float *v_pos, int V, const int32_t *tri,
+                                                               const float *v_tex, int Vt, const int32_t *tri_tex, int F,
+                                                               float4 *acc)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F) return;
+    const int i0 = __ldg(tri + 3 * (size_t)t), i1 = __ldg(tri + 3 * (size_t)t + 1), i2 = __ldg(tri + 3 * (size_t)t + 2);
+    const int j0 = __ldg(tri_tex + 3 * (size_t)t), j1 = __ldg(tri_tex + 3 * (size_t)t + 1), j2 = __ldg(tri_tex + 3 * (size_t)t + 2);
+    if ((unsigned)i0 >= (unsigned)V || (unsigned)i1 >= (unsigned)V || (unsigned)i2 >= (unsigned)V) return;
+    if ((unsigned)j0 >= (unsigned)Vt || (unsigned)j1 >= (unsigned)Vt || (unsigned)j2 >= (unsigned)Vt) return;
+    const float *p0 = v_pos + 3 * (size_t)i0, *p1 = v_pos + 3 * (size_t)i1, *p2 = v_pos + 3 * (size_t)i2;
+    const float *t0 = v_tex + 2 * (size_t)j0, *t1 = v_tex + 2 * (size_t)j1, *t2 = v_tex + 2 * (size_t)j2;
+    const float u1 = __ldg(t1) - __ldg(t0), v1 = __ldg(t1 + 1) - __ldg(t0 + 1);
+    const float u2 = __ldg(t2) - __ldg(t0), v2 = __ldg(t2 + 1) - __ldg(t0 + 1);
+    float den = u1 * v2 - v1 * u2;
+    den = den > 0.0f ? fmaxf(den, 1e-6f) : fminf(den, -1e-6f);   // NaN stays NaN, as torch.clamp keeps it
+    float tg[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float e1 = __ldg(p1 + k) - __ldg(p0 + k), e2 = __ldg(p2 + k) - __ldg(p0 + k);
+        tg[k] = (e1 * v2 - e2 * v1) / den;
+    }
+    const int idx[3] = { i0, i1, i2 };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float *d = reinterpret_cast<float *>(acc + idx[k]);
+        atomicAdd(d, tg[0]); atomicAdd(d + 1, tg[1]); atomicAdd(d + 2, tg[2]); atomicAdd(d + 3, 1.0f);
+    }
+}
+
+__device__ __forceinline__ void normalize3(float &x, float &y, float &z)
+{
+    const float d = fmaxf(sqrtf((x * x + y * y) + z * z), 1e-12f);   // F.normalize: x / max(|x|, eps)
+    x = x / d; y = y / d; z = z / d;
+}
+
+__global__ void __launch_bounds__(256) k_finish_vertex_tangents(const float4 *acc, const float *v_nrm, int V, float *out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float4 a = acc[v];
+    float x = a.x / a.w, y = a.y / a.w, z = a.z / a.w;   // a vertex without a face: 0 / 0, as in the reference
+    normalize3(x, y, z);
+    const float nx = __ldg(v_nrm + 3 * (size_t)v), ny = __ldg(v_nrm + 3 * (size_t)v + 1), nz = __ldg(v_nrm + 3 * (size_t)v + 2);
+    const float d = (x * nx + y * ny) + z * nz;
+    x = x - d * nx; y = y - d * ny; z = z - d * nz;
+    normalize3(x, y, z);
+    out[3 * (size_t)v] = x; out[3 * (size_t)v + 1] = y; out[3 * (size_t)v + 2] = z;
+}
+
+// ------------------------------------------------------------------------------------------
+// Normal maps of the views -> UV tangent space (mvadapter/test/utils/pipeline_texture.py:358-396): the view's
+// normal image is read in the geometry tangent frame of its camera (a per-view axis `gt`, Gram-Schmidt against
+// the rendered normal), turned into a world-space normal and then expressed in the (tangent, bitangent, normal)
+// frame rendered from the mesh; output in [0, 1].  One thread per pixel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cross3(float ax, float ay, float az, float bx, float by, float bz, float &x, float &y, float &z)
+{
+    x = ay * bz - az * by; y = az * bx - ax * bz; z = ax * by - ay * bx;
+}
+
+__global__ void __launch_bounds__(256) k_tangent_space_normals(const float *normal, const float *tangent, const float *image,
+                                                               const float *view_axis, long long total, long long npix_view,
+                                                               float *out)
+{
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const int b = (int)(o / npix_view);
+    const float nx = normal[3 * o], ny = normal[3 * o + 1], nz = normal[3 * o + 2];
+    const float tx = tangent[3 * o], ty = tangent[3 * o + 1], tz = tangent[3 * o + 2];
+    // UV tangent frame: rows T, B = N x T, N, each normalised
+    float bx, by, bz;
+    cross3(nx, ny, nz, tx, ty, tz, bx, by, bz);
+    float Tx = tx, Ty = ty, Tz = tz, Bx = bx, By = by, Bz = bz, Nx = nx, Ny = ny, Nz = nz;
+    normalize3(Tx, Ty, Tz); normalize3(Bx, By, Bz); normalize3(Nx, Ny, Nz);
+    // geometry tangent frame: GB = N x gt, GT = GB x N, rows GT, GB, N normalised
+    const float gx = view_axis[3 * b], gy = view_axis[3 * b + 1], gz = view_axis[3 * b + 2];
+    float hx, hy, hz, ux, uy, uz;
+    cross3(nx, ny, nz, gx, gy, gz, hx, hy, hz);
+    cross3(hx, hy, hz, nx, ny, nz, ux, uy, uz);
+    normalize3(ux, uy, uz); normalize3(hx, hy, hz);
+    // world-space normal = sum_j m_j * row_j of the geometry frame
+    const float m0 = image[3 * o] * 2.0f - 1.0f, m1 = image[3 * o + 1] * 2.0f - 1.0f, m2 = image[3 * o + 2] * 2.0f - 1.0f;
+    float wx = (m0 * ux + m1 * hx) + m2 * Nx, wy = (m0 * uy + m1 * hy) + m2 * Ny, wz = (m0 * uz + m1 * hz) + m2 * Nz;
+    normalize3(wx, wy, wz);
+    // components in the UV tangent frame
+    float rx = (wx * Tx + wy * Ty) + wz * Tz, ry = (wx * Bx + wy * By) + wz * Bz, rz = (wx * Nx + wy * Ny) + wz * Nz;
+    normalize3(rx, ry, rz);
+    out[3 * o] = fminf(fmaxf(rx * 0.5f + 0.5f, 0.0f), 1.0f);
+    out[3 * o + 1] = fminf(fmaxf(ry * 0.5f + 0.5f, 0.0f), 1.0f);
+    out[3 * o + 2] = fminf(fmaxf(rz * 0.5f + 0.5f, 0.0f), 1.0f);
+}
+
 }  // namespace
 
 extern "C" int wr_interpolate(wr_ctx *ctx, const float *attr, int attr_B, int V, int A, const float *rast, int B,
@@ -144,3 +243,42 @@ extern "C" int wr_vertex_normals(wr_ctx *ctx, const float *v_pos, int V, const i
     return WR_OK;
 }
 
+
+extern "C" int wr_vertex_tangents(wr_ctx *ctx, const float *v_pos, int V, const int32_t *tri, const float *v_tex, int Vt,
+                                  const int32_t *tri_tex, int F, const float *v_nrm, float *v_tang, void *stream_)
+{
+    if (!ctx || V < 0 || F < 0 || Vt < 0) return WR_ERR_INVALID_ARGUMENT;
+    if (V == 0) return WR_OK;
+    if (!v_pos || !v_nrm || !v_tang || (F > 0 && (!tri || !tri_tex || !v_tex))) return WR_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
+    int rc = wr_scratch_reserve(ctx, (size_t)V * sizeof(float4), stream);
+    if (rc != WR_OK) return rc;
+    ctx->clean_bytes = 0;  // the accumulators overwrite the head of the scratch
+    float4 *acc = static_cast<float4 *>(ctx->scratch);
+    e = cudaMemsetAsync(acc, 0, (size_t)V * sizeof(float4), stream);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset tangents");
+    if (F > 0) {
+        k_face_tangents_scatter<<<wr_div_up(F, 256), 256, 0, stream>>>(v_pos, V, tri, v_tex, Vt, tri_tex, F, acc);
+        WR_CHECK_LAUNCH(ctx, "k_face_tangents_scatter");
+    }
+    k_finish_vertex_tangents<<<wr_div_up(V, 256), 256, 0, stream>>>(acc, v_nrm, V, v_tang);
+    WR_CHECK_LAUNCH(ctx, "k_finish_vertex_tangents");
+    return WR_OK;
+}
+
+extern "C" int wr_tangent_space_normals(wr_ctx *ctx, const float *normal, const float *tangent, const float *image,
+                                        const float *view_axis, int B, int H, int W, float *out, void *stream_)
+{
+    if (!ctx || B < 0 || H <= 0 || W <= 0) return WR_ERR_INVALID_ARGUMENT;
+    if (B == 0) return WR_OK;
+    if (!normal || !tangent || !image || !view_axis || !out) return WR_ERR_INVALID_ARGUMENT;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
+    const long long npv = (long long)H * W, total = npv * B;
+    k_tangent_space_normals<<<wr_div_up(total, 256), 256, 0, stream>>>(normal, tangent, image, view_axis, total, npv, out);
+    WR_CHECK_LAUNCH(ctx, "k_tangent_space_normals");
+    return WR_OK;
+}

@@ -131,28 +131,32 @@ class TexturedMesh:
         return out
 
     def _compute_tangent(self) -> torch.Tensor:
-        """Per-vertex tangents from UV gradients (mesh.py:121-167).  Not on the hot path: torch ops."""
-        tri_p, tri_t = self.t_pos_idx.long(), self.t_tex_idx.long()
-        p = [self.v_pos[tri_p[:, k]] for k in range(3)]
-        t = [self.v_tex[tri_t[:, k]] for k in range(3)]
+        """Per-vertex tangents from the UV gradients of the faces (mesh.py:121-167), on the GPU
+        (k_face_tangents_scatter / k_finish_vertex_tangents through wr_vertex_tangents)."""
         nrm = self.v_nrm
-        duv1, duv2 = t[1] - t[0], t[2] - t[0]
-        dp1, dp2 = p[1] - p[0], p[2] - p[0]
-        numer = dp1 * duv2[..., 1:2] - dp2 * duv1[..., 1:2]
-        det = duv1[..., 0:1] * duv2[..., 1:2] - duv1[..., 1:2] * duv2[..., 0:1]
-        det = torch.where(det > 0.0, torch.clamp(det, min=1e-6), torch.clamp(det, max=-1e-6))
-        face_tang = numer / det
-        acc = torch.zeros_like(nrm)
-        cnt = torch.zeros_like(nrm)
-        for k in range(3):
-            idx = tri_p[:, k][:, None].repeat(1, 3)
-            acc.scatter_add_(0, idx, face_tang)
-            cnt.scatter_add_(0, idx, torch.ones_like(face_tang))
-        tang = F.normalize(acc / cnt, dim=1)
-        tang = F.normalize(tang - dot(tang, nrm) * nrm, dim=1)
+        if nrm.device.type != "cuda":
+            raise RuntimeError("TexturedMesh.v_tang: tangents are computed by a CUDA kernel; move the mesh to a CUDA "
+                               "device first (mesh.to('cuda')). There is no CPU path.")
+        if self.v_tex is None or self.t_tex_idx is None:
+            raise ValueError("TexturedMesh.v_tang needs UV coordinates (v_tex, t_tex_idx)")
+        v = self.v_pos.to(torch.float32).contiguous()
+        vt = self.v_tex.to(torch.float32).contiguous()
+        tri, tri_t = self.index_i32("t_pos_idx"), self.index_i32("t_tex_idx")
+        if nrm.shape != v.shape:
+            raise ValueError("v_tang: v_nrm must have one row per vertex of v_pos (mesh.py:131 accumulates into "
+                             "zeros_like(v_nrm) by position index)")
+        if tri.shape != tri_t.shape:
+            raise ValueError("t_pos_idx and t_tex_idx must list the same faces")
+        nrm = nrm.to(torch.float32).contiguous()
+        out = torch.empty_like(v)
+        ctx = _shared_context(v.device)
+        ctx.check(_native.lib().wr_vertex_tangents(ctx.handle, _native.ptr(v), v.shape[0], _native.ptr(tri),
+                                                   _native.ptr(vt), vt.shape[0], _native.ptr(tri_t), tri.shape[0],
+                                                   _native.ptr(nrm), _native.ptr(out), ctx.stream()),
+                  "wr_vertex_tangents")
         if torch.is_anomaly_enabled():
-            assert torch.all(torch.isfinite(tang))
-        return tang
+            assert torch.all(torch.isfinite(out))
+        return out
 
     def to(self, device: Optional[str] = None):
         for name in ("v_pos", "t_pos_idx", "v_tex", "t_tex_idx", "texture", "_stitched_v_pos",
