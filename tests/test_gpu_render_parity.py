@@ -291,3 +291,75 @@ def test_empty_mesh_renders_background(wr_ctx):
     out = wr.render(wr_ctx, mesh, cam, 32, 48, render_attr=False, normal_background=0.5)
     assert not bool(out.mask.any()) and float(out.pos.abs().max()) == 0.0
     assert float((out.normal - 0.5).abs().max()) == 0.0 and float(out.depth.abs().max()) == 0.0
+
+
+def test_guards_autograd_face_count_and_rast_id_range(wr_ctx):
+    """Forward-only kernels refuse inputs that require grad (the reference is differentiable through nvdiffrast);
+    the normal / bake-view / tangent paths check that the stitched faces pair up with t_pos_idx; the float-encoded
+    triangle id of the rast tensor is refused beyond 2^24 faces."""
+    from worldrenderer_b200.render import render_geometry_raw
+    dev = wr_ctx.device
+    v, f = cases.icosphere_mesh(4)
+    mesh = make_mesh(v, f, dev)
+    cam = cases.canonical_cameras(device=dev)
+    mesh.v_pos.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        wr.render(wr_ctx, mesh, cam, 32, 32, render_attr=False)
+    with torch.no_grad():
+        out = wr.render(wr_ctx, mesh, cam, 32, 32, render_attr=False)
+    assert out.mask.any()
+    pos = torch.zeros(1, 4, 4, device=dev, requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        wr_ctx.rasterize(pos, torch.zeros(1, 3, dtype=torch.int32, device=dev), (8, 8))
+    mesh.v_pos.requires_grad_(False)
+    mesh.v_nrm
+    mesh._stitched_t_pos_idx = mesh.t_pos_idx[:-5].clone()   # fewer stitched faces than faces
+    for kw in (dict(want_geo=True, want_normal=False, want_pos=False,
+                    depth_normalization_strategy=wr.SimpleNormalization(scale=1.0, offset=0.0, clamp=False, bg_value=1e2)),
+               dict(want_normal=True)):
+        with pytest.raises(ValueError):
+            render_geometry_raw(wr_ctx, mesh, cam, 32, 32, **kw)
+    big = torch.zeros(((1 << 24) + 1, 3), dtype=torch.int32, device=dev)
+    with pytest.raises(NotImplementedError):
+        wr_ctx.rasterize(torch.zeros(1, 4, 4, device=dev), big, (8, 8))
+    _, ids = wr_ctx.rasterize_with_ids(torch.zeros(1, 4, 4, device=dev), big[: 1 << 20], (8, 8))
+    assert (ids == -1).all()
+
+
+def test_config_a_full_size_bit_exact_against_oracle(wr_ctx):
+    """BASELINE config A at full size: 50k-face icosphere, canonical 6-view rig, 768^2 (the coarse-mesh path:
+    several lanes per triangle in the set-up kernel, 16-byte vertex records in the shading kernel)."""
+    v, f = cases.icosphere_mesh(50)
+    assert f.shape[0] == 50_000
+    mesh = make_mesh(v, f, wr_ctx.device)
+    cam = cases.canonical_cameras(device=wr_ctx.device)
+    raw = render_geometry_raw(wr_ctx, mesh, cam, 768, 768, want_tri_id=True,
+                              depth_normalization_strategy=wr.DepthControlNetNormalization())
+    ref = _oracle(mesh, cam, 768, 768, DepthSpec("controlnet"))
+    np.testing.assert_array_equal(raw["tri_id"].cpu().numpy(), ref["tri_id"])
+    np.testing.assert_array_equal(raw["mask"].cpu().numpy(), ref["mask"])
+    for k in ("pos", "normal", "depth"):
+        np.testing.assert_array_equal(raw[k].cpu().numpy(), ref[k], err_msg=k)
+    assert ref["mask"].sum() > 6 * 0.6 * 768 * 768   # a sphere of radius 0.5 in a 1.1-wide frame covers 65 %
+
+
+def test_config_e_share_bit_exact_against_oracle(wr_ctx):
+    """BASELINE config E, one GPU's share at full size: 5M-face terrain, 4 of the 32 ring views at 2048^2 -- triangle
+    ids, coverage, position, normal and depth identical to the CPU oracle (a few seconds of host time)."""
+    from worldrenderer_b200 import synth
+    v, f = synth.terrain(2500, 1000, 3)
+    assert f.shape[0] == 5_000_000
+    v = v / np.abs(v).max() * 0.5
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], -1).astype(np.float32)
+    mesh = make_mesh(v, f.astype(np.int32), wr_ctx.device)
+    az = [360.0 * k / 32 - 90.0 for k in (0, 9, 18, 27)]
+    cam = wr.get_orthogonal_camera(elevation_deg=[20.0] * 4, distance=[1.0] * 4, left=-0.55, right=0.55, bottom=-0.55,
+                                   top=0.55, azimuth_deg=az, device=str(wr_ctx.device))
+    spec = wr.SimpleNormalization(scale=1.0, offset=0.0, clamp=False, bg_value=1e2)
+    raw = render_geometry_raw(wr_ctx, mesh, cam, 2048, 2048, want_tri_id=True, depth_normalization_strategy=spec)
+    ref = _oracle(mesh, cam, 2048, 2048, DepthSpec("simple", scale=1.0, offset=0.0, clamp=False, bg_value=1e2))
+    np.testing.assert_array_equal(raw["tri_id"].cpu().numpy(), ref["tri_id"])
+    np.testing.assert_array_equal(raw["mask"].cpu().numpy(), ref["mask"])
+    for k in ("pos", "normal", "depth"):
+        np.testing.assert_array_equal(raw[k].cpu().numpy(), ref[k], err_msg=k)
+    assert ref["mask"].sum() > 4 * 0.2 * 2048 * 2048

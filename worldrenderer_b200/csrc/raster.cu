@@ -1060,6 +1060,9 @@ extern "C" int wr_rasterize(wr_ctx *ctx, const float *pos, int B, int V, int pos
 {
     if (!ctx || B < 0 || V < 0 || F < 0 || H <= 0 || W <= 0 || H > 8192 || W > 8192) return WR_ERR_INVALID_ARGUMENT;
     if (F >= (1 << 30)) return WR_ERR_UNSUPPORTED;
+    // the rast tensor carries the id as (float)(id + 1): exact up to 2^24 faces only (the triangle-id output has no
+    // such limit)
+    if (rast && F > (1 << 24)) return WR_ERR_UNSUPPORTED;
     if ((V > 0 && !pos) || (F > 0 && !tri)) return WR_ERR_INVALID_ARGUMENT;
     if (B == 0) return WR_OK;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

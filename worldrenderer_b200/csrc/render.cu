@@ -503,6 +503,7 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
     const wr_render_args &A = *args;
     if (A.B < 0 || A.V < 0 || A.F < 0 || A.H <= 0 || A.W <= 0 || A.H > 8192 || A.W > 8192) return WR_ERR_INVALID_ARGUMENT;
     if (A.F >= (1 << 30)) return WR_ERR_UNSUPPORTED;
+    if (A.out_rast && A.F > (1 << 24)) return WR_ERR_UNSUPPORTED;  // (float)(id + 1) is exact up to 2^24 faces
     if (A.B == 0) return WR_OK;
     if (!A.mvp || (A.V > 0 && !A.v_pos) || (A.F > 0 && !A.tri)) return WR_ERR_INVALID_ARGUMENT;
     if (reinterpret_cast<uintptr_t>(A.mvp) & 15u) return WR_ERR_INVALID_ARGUMENT;  // read as float4 rows

@@ -156,10 +156,19 @@ def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group) -> Optiona
     key = (uv_h, uv_w, device.index, id(group))
     ws = _P2P_WORKSPACES.get(key)
     if ws is None:
+        err = None
         try:
             ws = P2PBakeWorkspace(uv_h, uv_w, device, group)
-        except Exception as e:  # all ranks take the same branch: rendezvous is collective and fails everywhere
-            warnings.warn(f"peer-memory bake unavailable ({type(e).__name__}: {e}); using NCCL all_reduce")
+        except Exception as e:
+            ws, err = None, e
+        # symm_mem.empty is a LOCAL allocation: it can fail on one rank only (out of memory).  Agree on the outcome
+        # before anyone commits to a path, or that rank would sit in all_reduce while the others wait on the
+        # symmetric-memory barrier.
+        ok = torch.tensor([0 if ws is None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            why = f"{type(err).__name__}: {err}" if err is not None else "another rank could not set it up"
+            warnings.warn(f"peer-memory bake unavailable ({why}); using NCCL all_reduce")
             _P2P_DISABLED = True
             return None
         _P2P_WORKSPACES[key] = ws

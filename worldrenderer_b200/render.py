@@ -47,6 +47,15 @@ def _i32c(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.int32).contiguous()
 
 
+def _no_autograd(what: str, *tensors) -> None:
+    """The reference is differentiable through nvdiffrast; these kernels are forward-only.  A caller that optimises
+    through the result must hear about it instead of silently getting no gradient."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            f"{what}: an input requires grad, but worldrenderer_b200 is forward-only (no backward kernels). "
+            "Detach the inputs or call under torch.no_grad().")
+
+
 class NVDiffRastContextWrapper:
     """Same constructor and methods as the reference wrapper (render.py:30-149).
 
@@ -78,6 +87,7 @@ class NVDiffRastContextWrapper:
         return rast, rast.new_zeros(*rast.shape[:-1], 0)
 
     def rasterize_with_ids(self, pos, tri, resolution, ranges=None, want_ids=True):
+        _no_autograd("rasterize()", pos)
         pos = _f32c(pos)
         tri = _i32c(tri)
         self._check_device(pos, tri)
@@ -117,6 +127,7 @@ class NVDiffRastContextWrapper:
         """attr [1|B,V,A] or [V,A]; rast from rasterize(); tri [F,3] -> ([B,H,W,A], empty [B,H,W,0])."""
         if rast_db is not None and diff_attrs is not None:
             raise NotImplementedError("attribute derivatives (rast_db / diff_attrs) are outside the geometry path")
+        _no_autograd("interpolate()", attr, rast)
         attr = _f32c(attr)
         tri = _i32c(tri)
         rast = _f32c(rast)
@@ -144,6 +155,7 @@ class NVDiffRastContextWrapper:
             raise NotImplementedError("mip-mapped texture sampling is outside the geometry path")
         if filter_mode not in _FILTER_MODES or boundary_mode not in _BOUNDARY_MODES:
             raise NotImplementedError(f"texture: filter_mode={filter_mode!r}, boundary_mode={boundary_mode!r}")
+        _no_autograd("texture()", tex, uv)
         tex = _f32c(tex)
         uv = _f32c(uv)
         self._check_device(tex, uv)
@@ -261,6 +273,7 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
                         attr_background=0.5, texture_override=None, texture_filter_mode="linear"):
     """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool)."""
     dev = ctx.device
+    _no_autograd("render()", mesh.v_pos, cam.mvp_mtx, cam.w2c, mesh.texture if want_attr else None, texture_override)
     v_pos = _f32c(mesh.v_pos)
     tri = mesh.index_i32("t_pos_idx")
     mvp = _f32c(cam.mvp_mtx)
@@ -283,6 +296,11 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         a.depth_mode, a.depth_p0, a.depth_p1, a.depth_clamp, a.depth_bg = mode, p0, p1, clamp, bg
         out["depth"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         a.out_depth = _native.ptr(out["depth"])
+    if want_geo or want_normal or want_tangent:
+        # the kernel reads tri_nrm[3 * id] for every covered pixel: one row per face of t_pos_idx, or an
+        # out-of-bounds device read
+        if mesh.index_i32("stitched_t_pos_idx").shape[0] != tri.shape[0]:
+            raise ValueError("stitched_t_pos_idx must have one row per face of t_pos_idx")
     if want_geo:  # bake view map (pos.xyz, aoi_cos): needs the vertex normals but writes no normal map
         v_nrm = _f32c(mesh.v_nrm)
         tri_n = mesh.index_i32("stitched_t_pos_idx")
@@ -300,8 +318,6 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         v_nrm = _f32c(mesh.v_nrm)
         tri_n = mesh.index_i32("stitched_t_pos_idx")
         ctx._check_device(v_nrm, tri_n)
-        if tri_n.shape[0] != tri.shape[0]:
-            raise ValueError("stitched_t_pos_idx must have one row per face of t_pos_idx")
         keep += [v_nrm, tri_n]
         # a mesh that was not stitched shares one index tensor: the kernel then reuses the position indices
         same_faces = mesh._stitched_t_pos_idx is None or mesh._stitched_t_pos_idx is mesh.t_pos_idx
