@@ -138,3 +138,29 @@ def inside_cameras(device=None):
     import worldrenderer_b200 as wr
     return wr.get_camera(elevation_deg=[5.0, 40.0], distance=[0.3, 0.45], fovy_deg=[70.0, 90.0],
                          azimuth_deg=[20.0, 200.0], near=0.05, far=10.0, device=device)
+
+
+def huge_triangle_scene(seed: int = 31, n_huge: int = 300, n_small: int = 2000, n_clip: int = 12, B: int = 2):
+    """The tile pass of the LARGE class (csrc/raster.cu raster_tiles): hundreds of overlapping screen-sized triangles
+    (more than one 256-triangle batch per band, depth and id ties among them), a layer of tiny triangles in front of
+    and behind them (the tile owner's atomicMin must merge with what the set-up kernel already resolved), and a few
+    triangles that need geometric clipping (they stay with the stripe pass, concurrently)."""
+    rng = np.random.default_rng(seed)
+    huge = np.zeros((B, n_huge, 3, 4), f32)
+    huge[..., :2] = rng.uniform(-1.6, 1.6, (B, n_huge, 3, 2))
+    huge[..., 2] = rng.choice([-0.4, 0.0, 0.3, 0.6], (B, n_huge, 1))   # few distinct depths: ties decided by id
+    huge[..., 2] += rng.uniform(-0.3, 0.3, (B, n_huge, 3)) * (rng.random((B, n_huge, 1)) < 0.5)
+    huge[..., 3] = 1
+    c = rng.uniform(-1.0, 1.0, (B, n_small, 1, 2))
+    small = np.zeros((B, n_small, 3, 4), f32)
+    small[..., :2] = c + rng.uniform(-0.02, 0.02, (B, n_small, 3, 2))
+    small[..., 2] = rng.uniform(-0.9, 0.9, (B, n_small, 1))
+    small[..., 3] = 1
+    clip = np.zeros((B, n_clip, 3, 4), f32)
+    clip[..., :2] = rng.uniform(-1, 1, (B, n_clip, 3, 2))
+    clip[:, :, 1:, :2] *= 10.0 ** rng.uniform(2, 5, (B, n_clip, 2, 1))
+    clip[..., 2] = rng.uniform(-0.8, 0.8, (B, n_clip, 1))
+    clip[..., 3] = 1
+    pos = np.concatenate([huge.reshape(B, -1, 4), small.reshape(B, -1, 4), clip.reshape(B, -1, 4)], 1)
+    tri = np.arange(pos.shape[1], dtype=np.int32).reshape(-1, 3)
+    return pos.astype(f32), tri

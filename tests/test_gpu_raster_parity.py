@@ -97,6 +97,19 @@ def test_big_small_degenerate_mix(wr_ctx):
         _check(wr_ctx, pos, tri, res)
 
 
+@pytest.mark.parametrize("res", [(768, 1024), (333, 517), (2048, 2048)])
+def test_tile_pass_huge_triangles(wr_ctx, res):
+    """Hundreds of screen-sized triangles with depth ties, tiny triangles around them and clipped ones: the tile
+    pass (binning, per-band lists in shared memory, register resolve) against the oracle, bit for bit."""
+    pos, tri = cases.huge_triangle_scene()
+    rast, ids, ref = _check(wr_ctx, pos, tri, res)
+    np.testing.assert_array_equal(rast.view(np.uint32), ref.view(np.uint32))
+    assert (ids >= 0).mean() > 0.9 and len(np.unique(ids)) > 100
+    # only huge triangles, few of them (a single batch), and a box-like mesh through render()
+    pos, tri = cases.huge_triangle_scene(seed=5, n_huge=9, n_small=0, n_clip=0, B=1)
+    _check(wr_ctx, pos, tri, res)
+
+
 def test_large_viewport_4096(wr_ctx):
     pos, tri = cases.random_soup(11, 64, B=1)
     rast, ids = _gpu_rasterize(wr_ctx, pos, tri, (4096, 4096))

@@ -33,7 +33,8 @@ struct RasterParams {
     unsigned long long *depth;     // [B,H,W]
     uint32_t *queue;               // [B,Fq]
     int Fq;                        // queue stride (total triangle count)
-    int *counters;                 // [B,4]: 0 medium, 1 large
+    int *counters;                 // [B,4]: 0 medium queue length, 1 large queue length, 2 pixel-bbox area of the
+                                   // representable large triangles in units of 1024 pixels (one 32 x 32 tile)
 };
 
 __device__ __forceinline__ int floor_div16(int a) { return a >> 4; }
@@ -168,7 +169,7 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
 // right here (small), or to be queued (push = 1 medium, 2 large / to be clipped; entry = queue word).
 template <int LPT>
 __device__ __forceinline__ void setup_one(const RasterParams &P, const SnapVert &a, const SnapVert &c, const SnapVert &d,
-                                          int t, int sub, unsigned long long *depth_view, int &push, uint32_t &entry)
+                                          int t, int sub, unsigned long long *depth_view, int &push, uint32_t &entry, int b)
 {
     const int W = P.W, H = P.H;
     const uint32_t f_and = a.flags & c.flags & d.flags;
@@ -202,6 +203,7 @@ __device__ __forceinline__ void setup_one(const RasterParams &P, const SnapVert 
             } else if (sub == 0) {  // cannot happen for 64-px extents; kept for other thresholds
                 push = (npix <= kMediumMaxPix) ? 1 : 2;
                 entry = (uint32_t)(t + P.tri_base);
+                if (push == 2) atomicAdd(P.counters + 4 * b + 2, npix >> 10);
             }
         }
     } else if (sub == 0) {
@@ -209,6 +211,7 @@ __device__ __forceinline__ void setup_one(const RasterParams &P, const SnapVert 
         if (area2 != 0) {
             push = (npix <= kMediumMaxPix) ? 1 : 2;
             entry = (uint32_t)(t + P.tri_base);
+            if (push == 2) atomicAdd(P.counters + 4 * b + 2, npix >> 10);
         }
     }
 }
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) k_setup_triangles(RasterParams P, int vie
         if ((unsigned)i0 < (unsigned)P.V && (unsigned)i1 < (unsigned)P.V && (unsigned)i2 < (unsigned)P.V) {
             const SnapVert a = load_sv32(P.sv, vb + (unsigned)i0), c = load_sv32(P.sv, vb + (unsigned)i1),
                            d = load_sv32(P.sv, vb + (unsigned)i2);
-            setup_one<LPT>(P, a, c, d, t, sub, depth_view, push, entry);
+            setup_one<LPT>(P, a, c, d, t, sub, depth_view, push, entry, b);
         }
     }
     // warp-aggregated queue append: medium from the front, large / slow from the back
@@ -508,7 +511,10 @@ __device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsign
     int dx2 = x1 - x0, dy2 = y1 - y0;
     if (!(xmax - xmin < kSmallMaxExtent && ymax - ymin < kSmallMaxExtent && npix <= kSmallMaxPix)) {
         const long long a2 = (long long)dx2 * (y2 - y0) - (long long)dy2 * (x2 - x0);
-        if (a2 != 0) push = (npix <= kMediumMaxPix) ? 1 : 2;
+        if (a2 != 0) {
+            push = (npix <= kMediumMaxPix) ? 1 : 2;
+            if (push == 2) atomicAdd(P.counters + 4 * b + 2, npix >> 10);
+        }
         return;
     }
     int area2 = dx2 * (y2 - y0) - dy2 * (x2 - x0);  // extent below 2^10: exact in int32
@@ -574,7 +580,7 @@ __device__ __forceinline__ void mv_cold(const RasterParams &Pold, const VtxSrc &
     const SnapVert a = snap_one(wr_load_clip(src, b, i0), Pold.W, Pold.H);
     const SnapVert c = snap_one(wr_load_clip(src, b, i1), Pold.W, Pold.H);
     const SnapVert d = snap_one(wr_load_clip(src, b, i2), Pold.W, Pold.H);
-    setup_one<1>(Pold, a, c, d, t, 0, depth_view, push, entry);
+    setup_one<1>(Pold, a, c, d, t, 0, depth_view, push, entry, b);
 }
 
 #ifndef WR_MV_MINB
@@ -797,7 +803,8 @@ struct WarpClipScratch {
 };
 
 template <bool LARGE>
-__device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc &src, int b, WarpClipScratch *clip_smem)
+__device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc &src, int b, WarpClipScratch *clip_smem,
+                                             bool slow_only = false)
 {
     const unsigned lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -818,6 +825,7 @@ __device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc
         const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
                   i2 = __ldg(P.tri + 3 * (size_t)t + 2);
         if (!(entry & WR_QUEUE_SLOW)) {
+            if (slow_only) continue;  // the tile pass owns the representable large triangles of this view
             SnapVert a, c, d;
             if (P.sv) {
                 const size_t vb = (size_t)b * P.V;
@@ -863,15 +871,224 @@ __device__ __forceinline__ void raster_queue(const RasterParams &P, const VtxSrc
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tile pass for LARGE triangles (pixel bbox above kMediumMaxPix): binning + fine raster with the triangle lists of
+// a band of tiles staged in shared memory and the depth / id resolve in registers.
+//
+// A warp per triangle (the medium class) issues one global atomicMin per covered sample; for a triangle of a
+// million samples that is a million L2 atomics from 64 warps, with ~75 instructions per 8 x 4 footprint.  Here a
+// block OWNS a band of kTileBand 32 x 32-pixel tiles; inside a tile every thread keeps four pixels (a column strip
+// of four rows) of packed (depth key << 32 | id) values in registers.  The large queue of the view is walked in
+// batches of 256 triangles; per band and batch:
+//   stage   thread k fetches triangle k of the batch -- snapped vertices, orientation, 1 / area, z/w, the three
+//           edge functions at the band's first sample with their per-column / per-row steps -- into shared memory;
+//   bin     the same thread tests its triangle against the band's tiles: bounding box, then every edge at the tile
+//           corner where it is largest (the coarse reject); a warp ballot per tile turns the verdicts into the
+//           tile's triangle list, a 256-bit mask in shared memory;
+//   fine    tile after tile, all 256 threads walk the set bits of the tile's mask (broadcast reads) and test their
+//           four samples against each listed triangle: one addition and one comparison per edge and row, in int32
+//           when the triangle's extent keeps every value below 2^30 and in int64 otherwise (exact either way); a
+//           covered sample updates the thread's register copy;
+//   resolve every pixel that was hit does ONE atomicMin on the global buffer (it may already hold a nearer small
+//           triangle).
+// Two block barriers per band and batch.  Same integers, same float expressions as warp_raster_impl, and a
+// minimum is order independent, so results are identical bit for bit.  Triangles that need geometric clipping
+// (WR_QUEUE_SLOW) stay with the stripe pass; views with more than kTileMaxQueue large triangles too (every band
+// scans the whole queue, which stops paying off).
+constexpr int kTile = 32;
+constexpr int kTileBand = 8;
+constexpr int kTileMaxQueue = 2048;
+constexpr int kTileMinAvgTiles = 128;   // average pixel-bbox area of a large triangle, in tiles, from which the tile pass is used
+
+struct TileTri {         // one staged triangle, orientation normalised
+    long long e[3];      // edge functions at the sample of the band's first pixel
+    int sx[3], sy[3];    // step per column / per row
+    float inv_area, z[3];
+    uint32_t id;
+    uint32_t flags;      // bits 0-2: edge k excludes samples exactly on it; bit 3: int32 is exact around the band
+};
+
+struct TileScratch {
+    TileTri tri[256];
+    unsigned mask[kTileBand][8];   // tile, warp: which of the warp's 32 staged triangles are on the tile's list
+};
+
+template <typename E>
+__device__ __forceinline__ void tile_fine(const TileTri &T, int col, int ly, unsigned long long (&best)[4])
+{
+    E e0 = (E)T.e[0] + (E)T.sx[0] * col + (E)T.sy[0] * ly;
+    E e1 = (E)T.e[1] + (E)T.sx[1] * col + (E)T.sy[1] * ly;
+    E e2 = (E)T.e[2] + (E)T.sx[2] * col + (E)T.sy[2] * ly;
+    const E b0 = T.flags & 1u, b1 = (T.flags >> 1) & 1u, b2 = (T.flags >> 2) & 1u;
+    const float inv_area = T.inv_area, z0 = T.z[0], z1 = T.z[1], z2 = T.z[2];
+    const uint32_t id = T.id;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (e0 >= b0 && e1 >= b1 && e2 >= b2) {
+            const float w0 = edge_to_float<E>(e0) * inv_area;
+            const float w1 = edge_to_float<E>(e1) * inv_area;
+            const float w2 = (1.0f - w0) - w1;
+            float zw = ((z0 * w0) + (z1 * w1)) + (z2 * w2);
+            zw = zw + 0.0f;
+            if (zw >= -1.0f && zw <= 1.0f) {
+                const unsigned long long packed = ((unsigned long long)wr_depth_key(zw) << 32) | id;
+                best[j] = packed < best[j] ? packed : best[j];
+            }
+        }
+        e0 += (E)T.sy[0]; e1 += (E)T.sy[1]; e2 += (E)T.sy[2];
+    }
+}
+
+__device__ __forceinline__ void raster_tiles(const RasterParams &P, const VtxSrc &src, int b, int nlarge, TileScratch &S)
+{
+    const int W = P.W, H = P.H;
+    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
+    const int bands_x = (tiles_x + kTileBand - 1) / kTileBand;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lx = (int)lane, ly = (int)warp * 4;   // this thread's column and first row inside a tile
+    const uint32_t *qv = P.queue + (size_t)b * P.Fq;
+    unsigned long long *depth_view = P.depth + (size_t)b * H * W;
+#pragma unroll 1
+    for (int band = blockIdx.x; band < bands_x * tiles_y; band += gridDim.x) {
+        const int tx0 = (band % bands_x) * kTileBand, ty = band / bands_x;
+        const int ntx = min(kTileBand, tiles_x - tx0);
+        const int r0 = ty * kTile, r1 = min(r0 + kTile, H) - 1;
+        const int bc0 = tx0 * kTile, bc1 = min(bc0 + ntx * kTile, W) - 1;   // pixel columns of the band
+#pragma unroll 1
+        for (int base = 0; base < nlarge; base += 256) {
+            // ---- stage + bin: triangle base + tid, once per band
+            unsigned hit = 0;   // bit t: on the list of tile t of the band
+            const int qi = base + (int)tid;
+            if (qi < nlarge) {
+                const uint32_t entry = qv[P.Fq - 1 - qi];
+                if (!(entry & WR_QUEUE_SLOW)) {
+                    const int t = (int)entry - P.tri_base;
+                    const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1),
+                              i2 = __ldg(P.tri + 3 * (size_t)t + 2);
+                    SnapVert a, c, d;
+                    if (P.sv) {
+                        const size_t vb = (size_t)b * P.V;
+                        a = load_sv(P.sv, vb + i0); c = load_sv(P.sv, vb + i1); d = load_sv(P.sv, vb + i2);
+                    } else {
+                        a = snap_one(wr_load_clip(src, b, i0), W, H);
+                        c = snap_one(wr_load_clip(src, b, i1), W, H);
+                        d = snap_one(wr_load_clip(src, b, i2), W, H);
+                    }
+                    int x0 = a.x, y0 = a.y, x1 = c.x, y1 = c.y, x2 = d.x, y2 = d.y;
+                    float z0 = a.zw, z1 = c.zw, z2 = d.zw;
+                    long long area2 = (long long)(x1 - x0) * (y2 - y0) - (long long)(y1 - y0) * (x2 - x0);
+                    if (area2 < 0) {
+                        int ti; float tf;
+                        ti = x1; x1 = x2; x2 = ti;
+                        ti = y1; y1 = y2; y2 = ti;
+                        tf = z1; z1 = z2; z2 = tf;
+                        area2 = -area2;
+                    }
+                    const int xmin = min(x0, min(x1, x2)), xmax = max(x0, max(x1, x2));
+                    const int ymin = min(y0, min(y1, y2)), ymax = max(y0, max(y1, y2));
+                    const int cl = max(ceil_div16(xmin), bc0), ch = min(floor_div16(xmax), bc1);
+                    const int rl = max(ceil_div16(ymin), r0), rh = min(floor_div16(ymax), r1);
+                    if (area2 != 0 && cl <= ch && rl <= rh) {
+                        const int vx[3] = { x0, x1, x2 }, vy[3] = { y0, y1, y2 };
+                        const int pyl = 16 * rl, pyh = 16 * rh;
+                        TileTri T;
+                        // int32 is exact while every value stays below 2^31: extent < 2^14 plus the band (2^12 + 2^9)
+                        T.flags = (xmax - xmin < 16384 && ymax - ymin < 16384) ? 8u : 0u;
+                        hit = ((1u << (ch / kTile - tx0 + 1)) - 1u) & ~((1u << (cl / kTile - tx0)) - 1u);  // bbox columns
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;   // edge k runs from vertex k1 to vertex k2
+                            const int dx = vx[k2] - vx[k1], dy = vy[k2] - vy[k1];
+                            const long long bias = top_left(dx, dy) ? 0 : 1;
+                            T.flags |= (uint32_t)bias << k;
+                            T.e[k] = (long long)dx * (16 * r0 - vy[k1]) - (long long)dy * (16 * bc0 - vx[k1]);
+                            T.sx[k] = -16 * dy;
+                            T.sy[k] = 16 * dx;
+                            // coarse reject per tile: the edge at the corner of the clipped box where it is largest
+                            const long long my = (long long)dx * ((dx >= 0 ? pyh : pyl) - vy[k1]);
+                            for (int tt = 0; tt < ntx; ++tt) {
+                                if (!(hit >> tt & 1u)) continue;
+                                const int tcl = max(cl, bc0 + tt * kTile), tch = min(ch, bc0 + tt * kTile + kTile - 1);
+                                const long long m = my - (long long)dy * ((dy >= 0 ? 16 * tcl : 16 * tch) - vx[k1]);
+                                if (m < bias) hit &= ~(1u << tt);
+                            }
+                        }
+                        if (hit) {
+                            T.inv_area = 1.0f / __ll2float_rn(area2);
+                            T.z[0] = z0; T.z[1] = z1; T.z[2] = z2;
+                            T.id = entry;
+                            S.tri[tid] = T;
+                        }
+                    }
+                }
+            }
+            unsigned any = 0;
+#pragma unroll
+            for (int tt = 0; tt < kTileBand; ++tt) {
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, (hit >> tt) & 1u);
+                if (lane == 0) S.mask[tt][warp] = m;
+                any |= m;
+            }
+            if (__syncthreads_or(any != 0) == 0) continue;   // nothing of this batch touches the band
+            // ---- fine + resolve, tile after tile
+#pragma unroll 1
+            for (int tt = 0; tt < ntx; ++tt) {
+                unsigned long long best[4] = { WR_EMPTY_PIXEL, WR_EMPTY_PIXEL, WR_EMPTY_PIXEL, WR_EMPTY_PIXEL };
+                const int col = tt * kTile + lx;   // column relative to the band
+                bool touched = false;
+#pragma unroll 1
+                for (int w = 0; w < 8; ++w) {
+                    unsigned bits = S.mask[tt][w];
+                    touched |= bits != 0;
+                    while (bits) {
+                        const TileTri &Ts = S.tri[32 * w + __ffs(bits) - 1];
+                        bits &= bits - 1u;
+                        if (Ts.flags & 8u) tile_fine<int>(Ts, col, ly, best);
+                        else tile_fine<long long>(Ts, col, ly, best);
+                    }
+                }
+                const int cx = bc0 + col;
+                if (touched && cx <= bc1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ry = r0 + ly + j;
+#ifdef WR_TILE_PLAIN
+                        if (ry <= r1 && best[j] != WR_EMPTY_PIXEL) {
+                            unsigned long long *q = depth_view + ((size_t)ry * W + cx);
+                            const unsigned long long cur = *q;
+                            if (best[j] < cur) *q = best[j];
+                        }
+#else
+                        if (ry <= r1 && best[j] != WR_EMPTY_PIXEL) atomicMin(depth_view + ((size_t)ry * W + cx), best[j]);
+#endif
+                    }
+                }
+            }
+            __syncthreads();   // the lists have been consumed: the next batch may overwrite them
+        }
+    }
+}
+
 // Medium queue (one warp per triangle) then large / clipped queue (64 warps per triangle) in one launch.
-__global__ void __launch_bounds__(256) k_raster_queues(RasterParams P, VtxSrc src, int view0)
+__global__ void __launch_bounds__(256, 3) k_raster_queues(RasterParams P, VtxSrc src, int view0)
 {
     __shared__ WarpClipScratch clip_smem[8];
+    __shared__ TileScratch tile_smem;
     wr_pdl_wait();
     wr_pdl_trigger();
     const int b = blockIdx.y + view0;
     raster_queue<false>(P, src, b, clip_smem);
-    raster_queue<true>(P, src, b, clip_smem);
+    // large triangles: the tile pass when the view queued few enough of them (WR_TILES=0 keeps the stripe pass)
+#ifndef WR_TILES
+#define WR_TILES 1
+#endif
+    // The tile pass pays off when the large triangles are large against a tile (measured, tools/exp_big.py: from
+    // ~128 tiles of pixel bounding box per triangle on average); below that the stripe pass' parallelism wins.
+    const int nlarge = P.counters[4 * b + 1];
+    const bool tiles = WR_TILES && nlarge > 0 && nlarge <= kTileMaxQueue &&
+                       (long long)P.counters[4 * b + 2] >= (long long)kTileMinAvgTiles * nlarge;
+    raster_queue<true>(P, src, b, clip_smem, tiles);
+    if (tiles) raster_tiles(P, src, b, nlarge, tile_smem);
 }
 
 // (u, v, z/w) of the winning triangle at a pixel centre from the unsnapped clip-space vertices
