@@ -578,8 +578,10 @@ def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
         arg = omega[None, :, 0, None, None] * x + omega[None, :, 1, None, None] * y + phi[:, :, None, None]
         return (0.5 + 0.5 * torch.sin(arg)).permute(0, 2, 3, 1).contiguous()
 
-    lo, hi = parallel.shard_bounds(NV, world)[rank]
-    images = images_for(lo, hi)
+    # interleaved view shards (rank, rank + world, ...): neighbouring ring views cost alike, so contiguous blocks
+    # leave the ranks unevenly loaded (tools/bake_balance_probe.py)
+    mine = parallel.shard_slice(NV, rank, world, interleave=True)
+    images = images_for(0, NV)[mine].contiguous() if world > 1 else images_for(0, NV)
     kw = dict(aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1, uv_exp_blend_alpha=3.0)
 
     def sync():
@@ -620,9 +622,9 @@ def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
             res["algorithmic_bytes_per_bake"] = bytes_bake
             res["frac_of_hbm_peak"] = bytes_bake / (ms * 1e-3) / 1e9 / peak
             return res
-        ms_auto, (atlas, any_) = time_bake("auto", cam[lo:hi], images)
+        ms_auto, (atlas, any_) = time_bake("auto", cam[mine], images)
         atlas, any_ = atlas.clone(), any_.clone()
-        ms_nccl, (atlas_n, any_n) = time_bake("nccl", cam[lo:hi], images)
+        ms_nccl, (atlas_n, any_n) = time_bake("nccl", cam[mine], images)
         # the exchange step alone, on this bake's accumulators
         ws = parallel._p2p_workspace(UV, UV, dev, None)
         exch = {}
@@ -652,6 +654,26 @@ def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
                 exch[name] = float(t.item())
             exch["kernel"] = "k_uv_reduce_finalize_mc (multimem.ld_reduce / multimem.st)" if (ws.mc_ptr and world >= 4) \
                 else "k_uv_reduce_finalize_p2p (peer loads / stores)"
+        # batched baking: a stream of bakes through parallel.BakePipeline (the exchange of bake k on its own stream,
+        # under the view passes of bake k + 1)
+        pipe = parallel.BakePipeline(ctx, UV, depth=2)
+        NB = 8
+        for _ in range(2):
+            tickets = [pipe.submit(mesh, cam[mine], images, **kw) for _ in range(3)]
+            atlas_p, any_p = tickets[-1].result()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tickets = [pipe.submit(mesh, cam[mine], images, **kw) for _ in range(NB)]
+        for tk in tickets:
+            atlas_p, any_p = tk.result()
+        e1.record()
+        torch.cuda.synchronize()
+        tp = torch.tensor([e0.elapsed_time(e1) / NB], dtype=torch.float64, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ms_pipe = float(tp.item())
+        pipe_same = bool(torch.equal(atlas_p, atlas) and torch.equal(any_p, any_))
+        sync()
         # rank 0 bakes all views alone: the 1-rank time of THIS run and the result to compare with
         same_mask, max_err, ms_one = True, 0.0, None
         if rank == 0:
@@ -668,6 +690,10 @@ def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
                     "ms_per_bake_1_rank": ms_one, "mask_equal_to_1_rank": same_mask, "max_abs_err_vs_1_rank": max_err,
                     "ranks_identical": identical,
                     "strong_scaling_efficiency": None if ms_one is None else ms_one / (world * ms_auto),
+                    "batched": {"what": f"{NB} bakes back to back through parallel.BakePipeline (depth 2): the exchange "
+                                        "of bake k runs on its own stream under the view passes of bake k + 1",
+                                "ms_per_bake": ms_pipe, "same_result_as_single_bake": pipe_same,
+                                "scaling_efficiency": None if ms_one is None else ms_one / (world * ms_pipe)},
                     "nvlink_bytes_per_texel": {"fused_multicast": "20 B out (in-switch sum) + 13 B in", "nccl": "2 x 20 B"}})
     return res
 

@@ -229,6 +229,10 @@ typedef struct wr_p2p_reduce_args {
     const float *mc_accum;
     float *mc_attr;
     uint8_t *mc_valid;
+    /* Upper bound on the thread blocks of the exchange kernel (0 = 8 per SM, the fastest when it runs alone).  The
+       kernel is bound by NVLink, not by the SMs: a pipelined bake (parallel.BakePipeline) runs it with one or two
+       blocks per SM so that the next bake's view passes keep the rest of the GPU. */
+    int max_blocks;
 } wr_p2p_reduce_args;
 int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *args, void *stream);
 

@@ -168,6 +168,31 @@ def test_sharded_bake_single_process_equals_camera_projection(wr_ctx):
     assert lo == 2 and len(outs) == 1 and outs[0].mask.shape == (6, 64, 64)
 
 
+def test_bake_pipeline_single_process_equals_sharded_bake(wr_ctx):
+    """parallel.BakePipeline (exchange stage on its own stream, double-buffered) gives the bakes of sharded_bake, in
+    order, also when more bakes are in flight than the pipeline has slots."""
+    from worldrenderer_b200 import parallel
+    mesh, cam, images = _setup(wr_ctx.device)
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    imgs = [img, img.flip(0).contiguous(), (img * 0.5).contiguous(), img.roll(1, 0).contiguous(), img]
+    want = [tuple(t.clone() for t in parallel.sharded_bake(wr_ctx, mesh, cam, im, 128)) for im in imgs]
+    pipe = parallel.BakePipeline(wr_ctx, 128, depth=2)
+    got = []
+    for im in imgs:
+        tk = pipe.submit(mesh, cam, im)
+        got.append(tk)
+        if len(got) >= 2:   # consume with one bake in flight behind
+            a, m = got[-2].result()
+            got[-2] = (a.clone(), m.clone())
+    a, m = got[-1].result()
+    got[-1] = (a.clone(), m.clone())
+    torch.cuda.synchronize()
+    for (a, m), (wa, wm) in zip(got, want):
+        assert torch.equal(m, wm) and torch.equal(a, wa)
+    with pytest.raises(NotImplementedError):
+        pipe.submit(mesh, cam, img, uv_padding=True)
+
+
 def test_config_c_full_size_against_oracle(wr_ctx):
     """BASELINE config C at full size: 50k-face icosphere, 6 x 768^2 images -> 1024^2 atlas."""
     mesh, cam, images = _setup(wr_ctx.device, freq=50, views=(768, 768), uv_size=1024)

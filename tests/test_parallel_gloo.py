@@ -26,6 +26,19 @@ def test_shard_bounds_partition_everything_once():
             assert max(sizes) - min(sizes) <= 1
     assert parallel.my_shard(10, 1, 4) == (3, 6)
     assert parallel.my_shard(10) == (0, 10)  # no process group: one shard
+    # both kinds of shard_slice partition range(n); interleaved shards differ in size by at most one as well
+    for n in [0, 1, 7, 32]:
+        for world in [1, 3, 8]:
+            for il in (False, True):
+                parts = [list(range(n))[parallel.shard_slice(n, r, world, interleave=il)] for r in range(world)]
+                assert sorted(sum(parts, [])) == list(range(n))
+                assert max(map(len, parts)) - min(map(len, parts)) <= 1
+    assert list(range(32))[parallel.shard_slice(32, 3, 8, interleave=True)] == [3, 11, 19, 27]
+    import worldrenderer_b200 as wr
+    from worldrenderer_b200 import synth
+    cam = wr.get_orthogonal_camera(**synth.CANONICAL_RIG)
+    assert torch.equal(parallel.shard_camera(cam, 1, 2, interleave=True).mvp_mtx, cam.mvp_mtx[1::2])
+    assert torch.equal(parallel.shard_camera(cam, 1, 2).mvp_mtx, cam.mvp_mtx[3:6])
 
 
 def _free_port():

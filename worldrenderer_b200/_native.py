@@ -77,6 +77,7 @@ class P2PReduceArgs(ctypes.Structure):
         ("out_valid", ctypes.c_void_p * MAX_P2P_RANKS), ("old_attr", ctypes.c_void_p),
         ("world", ctypes.c_int), ("rank", ctypes.c_int), ("Hu", ctypes.c_int), ("Wu", ctypes.c_int),
         ("mc_accum", ctypes.c_void_p), ("mc_attr", ctypes.c_void_p), ("mc_valid", ctypes.c_void_p),
+        ("max_blocks", ctypes.c_int),
     ]
 
 

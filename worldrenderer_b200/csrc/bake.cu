@@ -362,6 +362,10 @@ __global__ void __launch_bounds__(256) k_grid_sample(const float *map, int H, in
 // is 20 B in (reduce-scatter) + 13 B out (all-gather of the result).
 constexpr int kP2PTexelsPerBlock = 1024;  // 256 threads x 4 texels
 
+// NR: upper bound on the ranks of this instantiation (2, 4, 8, 16): the NR loads of a chunk are in flight together,
+// so the register footprint follows the world size (128 registers at NR = 16 -- two resident blocks would own the
+// whole register file of an SM, which matters when the exchange runs under another bake's view passes).
+template <int NR>
 __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_args A, long long ntex, long long blk_lo,
                                                                 long long blk_hi)
 {
@@ -375,9 +379,9 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
         // fixed function of the owner of the texel, and only the owner computes it: results are reproducible
         // and identical on every rank.
         for (int j = threadIdx.x; j < nchunks; j += blockDim.x) {
-            float4 v[WR_MAX_P2P_RANKS];
+            float4 v[NR];
 #pragma unroll
-            for (int i = 0; i < WR_MAX_P2P_RANKS; ++i) {
+            for (int i = 0; i < NR; ++i) {
                 if (i < A.world) {
                     int r = A.rank + 1 + i;
                     if (r >= A.world) r -= A.world;
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
             }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < WR_MAX_P2P_RANKS; ++i)
+            for (int i = 0; i < NR; ++i)
                 if (i < A.world) { acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w; }
             s_sum[j] = acc;
         }
@@ -615,7 +619,10 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
     const long long nblk = (ntex + kP2PTexelsPerBlock - 1) / kP2PTexelsPerBlock;
     const long long blk_lo = nblk * A.rank / A.world, blk_hi = nblk * (A.rank + 1) / A.world;
     if (blk_hi > blk_lo) {
-        const int grid = (int)min(blk_hi - blk_lo, (long long)ctx->sm_count * 8);
+        // peer loads want many blocks in flight (8 per SM: 0.52 ms against 0.82 ms with one, 2 x B200, 4096^2); the
+        // multicast kernel is fastest with ONE per SM (0.595 against 0.635 ms with eight, 8 x B200)
+        int grid = (int)min(blk_hi - blk_lo, (long long)ctx->sm_count * (multicast ? 1 : 8));
+        if (A.max_blocks > 0) grid = min(grid, A.max_blocks);
         wr_stage_begin(ctx);
         if (multicast) {
             wr_stage(ctx, stream, "k_uv_reduce_finalize_mc");
@@ -623,7 +630,10 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
             WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_mc");
         } else {
             wr_stage(ctx, stream, "k_uv_reduce_finalize_p2p");
-            k_uv_reduce_finalize_p2p<<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            if (A.world <= 2) k_uv_reduce_finalize_p2p<2><<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            else if (A.world <= 4) k_uv_reduce_finalize_p2p<4><<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            else if (A.world <= 8) k_uv_reduce_finalize_p2p<8><<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            else k_uv_reduce_finalize_p2p<WR_MAX_P2P_RANKS><<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
             WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_p2p");
         }
         wr_stage(ctx, stream, "end");

@@ -16,6 +16,7 @@ BASELINE.json asks for:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import warnings
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -49,11 +50,25 @@ def my_shard(n: int, rank: Optional[int] = None, world: Optional[int] = None) ->
     return shard_bounds(n, world)[rank]
 
 
-def shard_camera(cam: Camera, rank: Optional[int] = None, world: Optional[int] = None) -> Camera:
+def shard_slice(n: int, rank: Optional[int] = None, world: Optional[int] = None, interleave: bool = False) -> slice:
+    """This rank's share of range(n) as a slice: a contiguous block (`shard_bounds`), or every world-th item
+    starting at `rank`.  Interleaving is the better split for the views of a camera ring: the cost of a view depends
+    on where it looks from, and neighbouring views cost alike, so contiguous blocks leave the ranks unevenly loaded
+    (config E on 8 GPUs: slowest rank 1.36 ms contiguous, 1.21 ms interleaved, mean 1.2 ms)."""
+    if rank is None or world is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world = 0, 1
+    if interleave:
+        return slice(rank, n, world)
+    lo, hi = shard_bounds(n, world)[rank]
+    return slice(lo, hi)
+
+
+def shard_camera(cam: Camera, rank: Optional[int] = None, world: Optional[int] = None, interleave: bool = False) -> Camera:
     """The views of `cam` owned by this rank (possibly an empty camera batch)."""
-    n = cam.mvp_mtx.shape[0]
-    lo, hi = my_shard(n, rank, world)
-    return cam[lo:hi]
+    return cam[shard_slice(cam.mvp_mtx.shape[0], rank, world, interleave)]
 
 
 def all_reduce_accumulators(accum: torch.Tensor, group=None) -> torch.Tensor:
@@ -111,7 +126,8 @@ class P2PBakeWorkspace:
     def barrier(self, channel: int) -> None:
         self.hdl.barrier(channel=channel)  # device-side, ordered on the current stream
 
-    def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor], multicast: Optional[bool] = None):
+    def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor], multicast: Optional[bool] = None,
+                        max_blocks: int = 0):
         """multicast: True / False force the NVSwitch multicast (multimem) or the peer load / store kernel; None
         picks multicast from 4 ranks up when the window exists (measured on 8 x B200, 4096^2 atlas: multicast
         0.64 ms, peer 1.19 ms, NCCL all_reduce + finalize 1.09 ms; on 2 ranks peer 0.52 ms, multicast 0.79 ms)."""
@@ -133,6 +149,7 @@ class P2PBakeWorkspace:
             old = old_attr.to(torch.float32).contiguous()
             a.old_attr = _native.ptr(old)
         a.world, a.rank, a.Hu, a.Wu = self.world, self.rank, self.uv_h, self.uv_w
+        a.max_blocks = int(max_blocks)
         self.barrier(0)  # every rank's accumulators are complete
         c = ctx.ctx
         c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()),
@@ -146,14 +163,15 @@ _P2P_WORKSPACES: Dict[tuple, "P2PBakeWorkspace"] = {}
 _P2P_DISABLED = False
 
 
-def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group) -> Optional["P2PBakeWorkspace"]:
-    """Workspace for (size, group), created on first use; None when peer memory is not usable (then NCCL)."""
+def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group, slot: int = 0) -> Optional["P2PBakeWorkspace"]:
+    """Workspace `slot` for (size, group), created on first use; None when peer memory is not usable (then NCCL).
+    A collective call the first time: every rank must ask for the same (size, group, slot) in the same order."""
     global _P2P_DISABLED
     if _P2P_DISABLED or not (dist.is_available() and dist.is_initialized()):
         return None
     if dist.get_backend(group) != "nccl" or dist.get_world_size(group) < 2 or (uv_h * uv_w) % 4 != 0:
         return None
-    key = (uv_h, uv_w, device.index, id(group))
+    key = (uv_h, uv_w, device.index, id(group), int(slot))
     ws = _P2P_WORKSPACES.get(key)
     if ws is None:
         err = None
@@ -198,7 +216,8 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
                  depth_grad_threshold: Optional[float] = 0.1, uv_exp_blend_alpha: float = 6.0,
                  uv_exp_blend_view_weight_local=None, group=None, exchange: str = "auto",
                  uv_padding: bool = False, poisson_blending: bool = False, pb_solver=None, pb_num_iters: int = 1000,
-                 pb_keep_original_border: bool = True, from_scratch: bool = False):
+                 pb_keep_original_border: bool = True, from_scratch: bool = False, _slot: int = 0,
+                 _exchange_stream: Optional["torch.cuda.Stream"] = None, _exchange_blocks: int = 0):
     """Config E: this rank holds `cam_local` / `images_local` (its share of the views, possibly none);
     the mesh is replicated.  Returns (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on all ranks.
 
@@ -214,7 +233,7 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
     if exchange not in ("auto", "p2p", "nccl"):
         raise ValueError(f"exchange={exchange!r}")
     pre = _uv_precompute_cached(ctx, mesh, uv_size)
-    ws = _p2p_workspace(uv_size, uv_size, ctx.device, group) if exchange != "nccl" else None
+    ws = _p2p_workspace(uv_size, uv_size, ctx.device, group, _slot) if exchange != "nccl" else None
     if exchange == "p2p" and ws is None:
         raise RuntimeError("exchange='p2p' requested but peer memory is not available for this process group")
     n_local = cam_local.mvp_mtx.shape[0]
@@ -230,13 +249,77 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
         accum.zero_()
     else:
         accum = torch.zeros((uv_size, uv_size, 5), dtype=torch.float32, device=ctx.device)
-    if ws is not None:
-        atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr)
-    else:
-        all_reduce_accumulators(accum, group)
-        atlas, valid_any = uv_finalize(ctx, accum, pre.uv_attr)
+    xs = _exchange_stream
+    if xs is not None:  # BakePipeline: the exchange (and everything after it) runs on its own stream
+        xs.wait_stream(torch.cuda.current_stream(ctx.device))
+        accum.record_stream(xs)
+    with torch.cuda.stream(xs) if xs is not None else contextlib.nullcontext():
+        if ws is not None:
+            atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr, max_blocks=_exchange_blocks)
+        else:
+            all_reduce_accumulators(accum, group)
+            atlas, valid_any = uv_finalize(ctx, accum, pre.uv_attr)
+    if xs is not None:
+        return atlas, valid_any
     if uv_padding or poisson_blending:
         atlas = atlas_postprocess(None, atlas, valid_any, pre, do_uv_padding=uv_padding, pad_unseen_area=from_scratch,
                                   poisson_blending=poisson_blending, pb_solver=pb_solver, pb_num_iters=pb_num_iters,
                                   pb_keep_original_border=pb_keep_original_border)
     return atlas, valid_any
+
+
+class BakeTicket:
+    """Result of one `BakePipeline.submit`: `result()` makes the current stream wait for the exchange and returns
+    (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on every rank.  With peer memory the tensors are views of a
+    pipeline slot: valid until `depth` more bakes have been submitted."""
+
+    def __init__(self, atlas, valid_any, done: "torch.cuda.Event", device):
+        self._atlas, self._valid, self._done, self._device = atlas, valid_any, done, device
+
+    def result(self):
+        torch.cuda.current_stream(self._device).wait_event(self._done)
+        return self._atlas, self._valid
+
+
+class BakePipeline:
+    """Batched multi-GPU baking (a stream of config-E bakes: SmartPainter rounds, a queue of meshes).
+
+    One bake on N ranks is [render + unproject this rank's views] -> [exchange the accumulators, finalise]: the first
+    part shrinks with N, the exchange does not (4096^2 x 20 B leave and 13 B reach every GPU over NVLink whatever N
+    is), so a single bake cannot scale past compute / (compute + exchange).  A batch can: the exchange of bake k runs
+    on its own stream, on pipeline slot k % depth (accumulators, atlas and barrier pads of its own in symmetric
+    memory), while the compute stream already renders bake k + 1.  Throughput is then bounded by the longer of the two
+    stages instead of their sum.  Every rank must submit the same bakes in the same order."""
+
+    def __init__(self, ctx, uv_size: int, depth: int = 2, group=None, exchange: str = "auto", exchange_blocks_per_sm: int = 1):
+        self.ctx, self.uv_size, self.depth, self.group, self.exchange = ctx, int(uv_size), max(1, int(depth)), group, exchange
+        # the exchange kernel with its default grid (8 blocks per SM) takes every thread slot of the GPU and, at
+        # high priority, simply runs INSTEAD of the next bake's view passes (measured: no overlap at all); it is bound
+        # by NVLink, so a block or two per SM moves the same bytes in about the same time and leaves the SMs alone
+        self._xblocks = max(1, int(exchange_blocks_per_sm)) * torch.cuda.get_device_properties(ctx.device).multi_processor_count
+        self.device = ctx.device
+        # high priority: the exchange kernel's blocks are placed as soon as SM slots free up instead of queueing
+        # behind every block the compute stream has already launched (it is NVLink-bound and needs few of them)
+        self._xs = torch.cuda.Stream(self.device, priority=-1)
+        self._done: List[Optional[torch.cuda.Event]] = [None] * self.depth
+        self._k = 0
+        if exchange != "nccl":   # collective set-up of every slot, up front and in the same order on all ranks
+            for slot in range(self.depth):
+                _p2p_workspace(self.uv_size, self.uv_size, self.device, group, slot)
+
+    def submit(self, mesh, cam_local: Camera, images_local: torch.Tensor, **bake_kwargs) -> BakeTicket:
+        for k in ("uv_padding", "poisson_blending"):
+            if bake_kwargs.get(k):
+                raise NotImplementedError("BakePipeline returns the exchanged atlas; run the post-processing tail on it")
+        slot = self._k % self.depth
+        self._k += 1
+        cur = torch.cuda.current_stream(self.device)
+        if self._done[slot] is not None:   # the slot's previous exchange must have drained before its accumulators are rewritten
+            cur.wait_event(self._done[slot])
+        atlas, valid_any = sharded_bake(self.ctx, mesh, cam_local, images_local, self.uv_size, group=self.group,
+                                        exchange=self.exchange, _slot=slot, _exchange_stream=self._xs,
+                                        _exchange_blocks=self._xblocks, **bake_kwargs)
+        done = torch.cuda.Event()
+        done.record(self._xs)
+        self._done[slot] = done
+        return BakeTicket(atlas, valid_any, done, self.device)
