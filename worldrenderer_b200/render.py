@@ -270,9 +270,22 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
                         want_pos=True, want_depth=True, want_normal=True, want_attr=False, want_tri_id=False,
                         want_rast=False, want_tangent=False, tangent_background=0.0, want_geo=False,
                         depth_normalization_strategy=None, normal_background=0.0,
-                        attr_background=0.5, texture_override=None, texture_filter_mode="linear"):
-    """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool)."""
+                        attr_background=0.5, texture_override=None, texture_filter_mode="linear", out_buffers=None):
+    """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool).
+    out_buffers: optional {name: preallocated contiguous tensor} written instead of fresh allocations (RenderGraph
+    renders groups of views into slices of one output)."""
     dev = ctx.device
+
+    def _new(name, shape, dtype):
+        buf = None if out_buffers is None else out_buffers.get(name)
+        if buf is None:
+            return torch.empty(shape, dtype=dtype, device=dev)
+        if buf.dtype == torch.bool and dtype == torch.uint8:
+            buf = buf.view(torch.uint8)
+        if tuple(buf.shape) != tuple(shape) or buf.dtype != dtype or buf.device != dev or not buf.is_contiguous():
+            raise ValueError(f"out_buffers[{name!r}]: expected a contiguous {dtype} tensor of shape {tuple(shape)} on {dev}")
+        return buf
+
     _no_autograd("render()", mesh.v_pos, cam.mvp_mtx, cam.w2c, mesh.texture if want_attr else None, texture_override)
     v_pos = _f32c(mesh.v_pos)
     tri = mesh.index_i32("t_pos_idx")
@@ -285,16 +298,16 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
     a.v_pos, a.tri, a.V, a.F = _native.ptr(v_pos), _native.ptr(tri), v_pos.shape[0], tri.shape[0]
     a.mvp, a.w2c, a.B, a.H, a.W = _native.ptr(mvp), _native.ptr(w2c), B, H, W
     out = {}
-    out["mask"] = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+    out["mask"] = _new("mask", (B, H, W), torch.uint8)
     a.out_mask = _native.ptr(out["mask"])
     if want_pos:
-        out["pos"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        out["pos"] = _new("pos", (B, H, W, 3), torch.float32)
         a.out_pos = _native.ptr(out["pos"])
     post = None
     if want_depth:
         mode, p0, p1, clamp, bg, post = _depth_kernel_params(depth_normalization_strategy)
         a.depth_mode, a.depth_p0, a.depth_p1, a.depth_clamp, a.depth_bg = mode, p0, p1, clamp, bg
-        out["depth"] = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        out["depth"] = _new("depth", (B, H, W), torch.float32)
         a.out_depth = _native.ptr(out["depth"])
     if want_geo or want_normal or want_tangent:
         # the kernel reads tri_nrm[3 * id] for every covered pixel: one row per face of t_pos_idx, or an
@@ -311,7 +324,7 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         a.tri_nrm = None if same_faces else _native.ptr(tri_n)
         nbg = _background_triplet(normal_background, "normal_background") or [0.0, 0.0, 0.0]
         a.normal_bg = (ctypes.c_float * 3)(*nbg)
-        out["geo"] = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        out["geo"] = _new("geo", (B, H, W, 4), torch.float32)
         a.out_geo = _native.ptr(out["geo"])
     nbg_tensor = None
     if want_normal:
@@ -327,7 +340,7 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         if nbg is None:
             nbg_tensor, nbg = normal_background, [0.0, 0.0, 0.0]
         a.normal_bg = (ctypes.c_float * 3)(*nbg)
-        out["normal"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        out["normal"] = _new("normal", (B, H, W, 3), torch.float32)
         a.out_normal = _native.ptr(out["normal"])
     tbg_tensor = None
     if want_tangent:
@@ -345,7 +358,7 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
         if tbg is None:
             tbg_tensor, tbg = tangent_background, [0.0, 0.0, 0.0]
         a.tangent_bg = (ctypes.c_float * 3)(*tbg)
-        out["tangent"] = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+        out["tangent"] = _new("tangent", (B, H, W, 3), torch.float32)
         a.out_tangent = _native.ptr(out["tangent"])
     abg_tensor = None
     if want_attr:
@@ -366,13 +379,13 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
             abg_tensor, a.attr_bg = attr_background, 0.0
         else:
             a.attr_bg = float(attr_background)
-        out["attr"] = torch.empty((B, H, W, tex.shape[2]), dtype=torch.float32, device=dev)
+        out["attr"] = _new("attr", (B, H, W, tex.shape[2]), torch.float32)
         a.out_attr = _native.ptr(out["attr"])
     if want_tri_id:
-        out["tri_id"] = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+        out["tri_id"] = _new("tri_id", (B, H, W), torch.int32)
         a.out_tri_id = _native.ptr(out["tri_id"])
     if want_rast:
-        out["rast"] = torch.empty((B, H, W, 4), dtype=torch.float32, device=dev)
+        out["rast"] = _new("rast", (B, H, W, 4), torch.float32)
         a.out_rast = _native.ptr(out["rast"])
     c = ctx.ctx
     c.check(_native.lib().wr_render(c.handle, ctypes.byref(a), c.stream()), "wr_render")
@@ -408,6 +421,7 @@ def render(
     tangent_background: Union[float, torch.Tensor] = 0.0,
     texture_override=None,
     texture_filter_mode: str = "linear",
+    _out_buffers=None,
 ) -> RenderOutput:
     """Same signature and outputs as the reference render() (render.py:220-286)."""
     if antialias_attr:
@@ -417,7 +431,7 @@ def render(
         want_attr=render_attr, want_tangent=render_tangent, tangent_background=tangent_background,
         depth_normalization_strategy=depth_normalization_strategy,
         normal_background=normal_background, attr_background=attr_background, texture_override=texture_override,
-        texture_filter_mode=texture_filter_mode)
+        texture_filter_mode=texture_filter_mode, out_buffers=_out_buffers)
     out = RenderOutput(mask=raw["mask"], pos=raw["pos"], depth=raw.get("depth"), attr=raw.get("attr"),
                        normal=raw.get("normal"))
     out.tangent = raw.get("tangent")
