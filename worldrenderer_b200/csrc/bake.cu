@@ -9,9 +9,44 @@
 //                      4 taps x 2 x 16-byte loads instead of 4 taps x (12 + 4 + 4 + 12) bytes
 //   k_uv_unproject     per texel: project into every view, gather, validity, weight, accumulate
 //   k_uv_finalize      stitch with the existing texture (after the optional all-reduce)
+#include <cuda.h>           // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+#include <cudaTypedefs.h>   // PFN_cuTensorMapEncodeTiled
+
 #include "common.cuh"
 
 namespace {
+
+// ---- TMA: the depth tile of k_view_prep (32 x 32 outputs + halo) is ONE cp.async.bulk.tensor load whose out-of-
+// bounds elements arrive as zeros -- which is exactly conv2d's zero padding, so the tile needs no bounds test.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy (TMA) must see the initialised barrier
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar))
+                 : "memory");
+}
 
 // View side of the bake in one pass.  A 32x32 output tile per 256-thread block; the depth tile (halo pad+1, zeros
 // outside the image = conv2d zero padding), the Sobel magnitude (halo pad, -inf outside the image =
@@ -24,17 +59,25 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
                                                                 const float *depth, const float *position,
                                                                 const float *w2c, const float *images, int H, int W,
                                                                 int dilation, float *aoi_out, float *depth_grad,
-                                                                float *geo_map, float *attr_map)
+                                                                float *geo_map, float *attr_map,
+                                                                const __grid_constant__ CUtensorMap depth_map, int use_tma)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
     wr_pdl_wait();   // dependent launch behind the shading kernel of the view pass (or whatever precedes it)
     wr_pdl_trigger();
     const int pad = dilation / 2;              // max-pool halo
     const int hd = pad + 1;                    // depth halo (Sobel needs one more ring)
-    const int dw = kPrepTW + 2 * hd, dh = kPrepTH + 2 * hd;
+    const int dh = kPrepTH + 2 * hd;
+    // The TMA box starts at a column that is a multiple of 4 (the innermost coordinate of a bulk tensor load must be
+    // 16-byte aligned -- measured: x = -3 or 61 is an illegal instruction, -4 works; rows are free) and is a whole
+    // number of 16-byte units wide: `lead` columns left of the tile instead of hd, row pitch dw.
+    const int lead = use_tma ? ((hd + 3) & ~3) : hd;
+    const int dw = use_tma ? ((lead + kPrepTW + hd + 3) & ~3) : kPrepTW + 2 * hd;
     const int gw = kPrepTW + 2 * pad, gh = kPrepTH + 2 * pad;
-    float *s_d = smem;                         // [dh][dw]
-    float *s_g = s_d + dh * dw;                // [gh][gw]
+    float *s_box = smem;                       // [dh][dw] as loaded
+    float *s_d = s_box + (lead - hd);          // logical tile: column 0 = image column x0 - hd
+    float *s_g = s_box + dh * dw;              // [gh][gw]
     float *s_r = s_g + gh * gw;                // [gh][kPrepTW] row maxima
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * kPrepTW, y0 = blockIdx.y * kPrepTH;
@@ -44,16 +87,28 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
         // (no integer division); the few halo columns beyond 32 are walked as one flat list by the whole block, so
         // that no pass runs with only a handful of lanes.
         const int tid = threadIdx.y * kPrepTW + threadIdx.x;
-        auto load_depth = [&](int ry, int rx) {
-            const int yy = y0 - hd + ry, xx = x0 - hd + rx;
-            s_d[ry * dw + rx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
-        };
-        for (int ry = threadIdx.y; ry < dh; ry += kPrepBH) load_depth(ry, threadIdx.x);
-        {
-            const int extra = dw - kPrepTW;
-            for (int e = tid; e < extra * dh; e += kPrepTW * kPrepBH) load_depth(e / extra, kPrepTW + e % extra);
+        if (use_tma) {
+            // one bulk tensor load of the [dh][dw] box at (x0 - hd, y0 - hd, b); elements outside the image are
+            // zero-filled by the hardware
+            if (tid == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, (unsigned)(dh * dw * sizeof(float)));
+                tma_load_3d(s_box, &depth_map, x0 - lead, y0 - hd, b, &s_bar);
+            }
+            mbar_wait(&s_bar, 0);
+        } else {
+            auto load_depth = [&](int ry, int rx) {
+                const int yy = y0 - hd + ry, xx = x0 - hd + rx;
+                s_d[ry * dw + rx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dv + (size_t)yy * W + xx) : 0.0f;
+            };
+            for (int ry = threadIdx.y; ry < dh; ry += kPrepBH) load_depth(ry, threadIdx.x);
+            {
+                const int extra = dw - kPrepTW;
+                for (int e = tid; e < extra * dh; e += kPrepTW * kPrepBH) load_depth(e / extra, kPrepTW + e % extra);
+            }
+            __syncthreads();
         }
-        __syncthreads();
         auto sobel = [&](int gy_, int gx_) {
             const int yy = y0 - pad + gy_, xx = x0 - pad + gx_;
             float g = -INFINITY;
@@ -544,7 +599,40 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
     const int pad = dilation / 2, hd = pad + 1;
-    const size_t smem = sizeof(float) * ((size_t)(kPrepTH + 2 * hd) * (kPrepTW + 2 * hd) +
+    // TMA needs 16-byte aligned rows (W % 4 == 0) and base; otherwise the block loads its tile by hand
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const int lead = (hd + 3) & ~3;
+    const int boxw = (lead + kPrepTW + hd + 3) & ~3, boxh = kPrepTH + 2 * hd;
+    int use_tma = 0;
+#ifndef WR_PREP_TMA
+#define WR_PREP_TMA 1
+#endif
+    if (WR_PREP_TMA && dilation > 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15u) == 0 && boxw <= 256 && boxh <= 256) {
+        static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+        static bool looked_up = false;
+        if (!looked_up) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+            else
+                cudaGetLastError();
+            looked_up = true;
+        }
+        if (encode) {
+            const cuuint64_t gdim[3] = { (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B };
+            const cuuint64_t gstride[2] = { (cuuint64_t)W * 4, (cuuint64_t)W * H * 4 };
+            const cuuint32_t box[3] = { (cuuint32_t)boxw, (cuuint32_t)boxh, 1 };
+            const cuuint32_t estride[3] = { 1, 1, 1 };
+            const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(depth), gdim, gstride, box,
+                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            use_tma = r == CUDA_SUCCESS ? 1 : 0;
+        }
+    }
+    const size_t smem = sizeof(float) * ((size_t)boxh * (use_tma ? boxw : kPrepTW + 2 * hd) +
                                          (size_t)(kPrepTH + 2 * pad) * (kPrepTW + 2 * pad) +
                                          (size_t)(kPrepTH + 2 * pad) * kPrepTW);
     if (smem > 48 * 1024) return WR_ERR_UNSUPPORTED;  // dilation > ~29
@@ -552,7 +640,7 @@ extern "C" int wr_view_prep(wr_ctx *ctx, const float *normal, const uint8_t *mas
     wr_stage_begin(ctx);
     wr_stage(ctx, stream, "k_view_prep");
     wr_launch_s(k_view_prep, grid, dim3(kPrepTW, kPrepBH), dilation > 0 ? smem : 0, stream, !ctx->profiling, normal, mask,
-                depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map);
+                depth, position, w2c, images, H, W, dilation, aoi_cos, depth_grad, geo_map, attr_map, tmap, use_tma);
     WR_CHECK_LAUNCH(ctx, "k_view_prep");
     wr_stage(ctx, stream, "end");
     return WR_OK;
