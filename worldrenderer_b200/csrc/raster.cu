@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
     if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    const bool finite_pos = isfinite(x) && isfinite(y) && isfinite(z);
     for (int b = 0; b < B; ++b) {
         float4 r0, r1, r2, r3;
         if (b < kStageViews) {
@@ -386,10 +387,23 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H
         c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
         c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
         c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
-        c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
-        unsigned rxy;
-        float rzw;
-        snap_rec(c, W, H, addx, addy, rxy, rzw);
+        unsigned rxy = 0u;
+        float rzw = 0.0f;
+        if (r3.x == 0.0f && r3.y == 0.0f && r3.z == 0.0f && r3.w == 1.0f) {
+            // Orthographic view (uniform branch).  For a finite vertex the contract's w = ((0 x + 0 y) + 0 z) + 1 is
+            // exactly 1, so snap_rec's unit-w expressions apply as they are; for a non-finite one 0 * inf = NaN fails
+            // its w > 0 test -- the explicit finiteness test (once per vertex) stands in for that.
+            if (finite_pos && c.z >= -1.0f && c.z <= 1.0f) {
+                const float fx = c.x * (float)(8 * W), fy = c.y * (float)(8 * H);
+                if (fabsf(fx) <= kRecLimit && fabsf(fy) <= kRecLimit) {
+                    rxy = (unsigned)(__float2int_rn(fx) + addx) | ((unsigned)(__float2int_rn(fy) + addy) << 16);
+                    rzw = c.z;
+                }
+            }
+        } else {
+            c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
+            snap_rec(c, W, H, addx, addy, rxy, rzw);
+        }
         rec[(size_t)b * src.V + v] = make_uint2(rxy, __float_as_uint(rzw));
     }
 }
