@@ -681,6 +681,11 @@ def bench_bake_sharded(ctx, dev, rank, world, flush_buf, full=True):
             ms_one, (atlas1, any1) = time_bake("nccl", cam, img_all, group_sync=False, reps=4, group=solo)
             same_mask = bool(torch.equal(any1, any_))
             max_err = float((atlas1 - atlas).abs().max())
+            dd = (atlas1 - atlas).abs().max(-1).values
+            iy, ix = divmod(int(dd.argmax()), UV)
+            print(f"[diag] texels > 1e-5: {int((dd > 1e-5).sum())}, > 1e-3: {int((dd > 1e-3).sum())}, max at {(iy, ix)}: "
+                  f"1-rank {atlas1[iy, ix].tolist()} N-rank {atlas[iy, ix].tolist()} nccl-path {atlas_n[iy, ix].tolist()} "
+                  f"any {bool(any1[iy, ix])}", file=sys.stderr, flush=True)
             del img_all
         sync()
         gathered = [torch.empty_like(atlas) for _ in range(world)]

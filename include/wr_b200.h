@@ -95,7 +95,8 @@ int wr_interpolate(wr_ctx *ctx, const float *attr, int attr_B, int V, int A, con
 int wr_texture(wr_ctx *ctx, const float *tex, int tex_B, int TH, int TW, int C, const float *uv, int B, int H,
                int W, int filter, int boundary, float *out, void *stream);
 
-/* mesh.py:85-119.  v_nrm: [V,3] out (used as the accumulator; float atomics => sum order varies). */
+/* mesh.py:85-119.  v_nrm: [V,3] out.  The face normals are summed exactly (64-bit fixed point in the context
+ * scratch), so the result does not depend on the order of the atomics: identical on every run, rank and GPU. */
 int wr_vertex_normals(wr_ctx *ctx, const float *v_pos, int V, const int32_t *tri, int F, float *v_nrm,
                       void *stream);
 

@@ -57,9 +57,36 @@ __global__ void __launch_bounds__(256) k_texture(const float *tex, int tex_B, in
 
 // ------------------------------------------------------------------------------------------
 // vertex normals (mesh.py:85-119)
+//
+// The reference splats the face normals with scatter_add_ (float atomics on the GPU: the sum order, and with it the
+// last bits of every normal, changes from run to run and from process to process).  Here the splat is EXACT and
+// therefore order independent: every face normal component -- computed in float exactly as there -- is converted
+// to 64-bit fixed point and added with integer atomics; the per-vertex sum is then rounded to float once.  Runs,
+// ranks and GPUs all see the same normals (a multi-GPU bake is then reproducible texel for texel: a validity test
+// on a normal-derived cosine can no longer flip between ranks), and each component is the correctly rounded sum.
+// Scale: 2^(50 - e) with 2^e >= 8 M^2 >= any face normal component (M = largest |coordinate|): 12 bits of headroom
+// for the faces around a vertex, 50 bits below the largest possible component.
 // ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_vertex_extent(const float *v_pos, long long n3, unsigned *extent_bits)
+{
+    float m = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (long long)gridDim.x * blockDim.x) {
+        const float a = fabsf(__ldg(v_pos + i));
+        if (a <= 3.402823466e38f) m = fmaxf(m, a);   // finite values only
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(extent_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+__device__ __forceinline__ int normal_scale_exp(unsigned extent_bits)
+{
+    int e;
+    frexpf(__uint_as_float(extent_bits), &e);   // M < 2^e
+    return 50 - (2 * e + 3);                    // 8 M^2 < 2^(2e + 3)
+}
+
 __global__ void __launch_bounds__(256) k_face_normals_scatter(const float *v_pos, int V, const int32_t *tri, int F,
-                                                              float *acc)
+                                                              long long *acc, const unsigned *extent_bits)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= F) return;
@@ -68,25 +95,43 @@ __global__ void __launch_bounds__(256) k_face_normals_scatter(const float *v_pos
     const float *p0 = v_pos + 3 * (size_t)i0, *p1 = v_pos + 3 * (size_t)i1, *p2 = v_pos + 3 * (size_t)i2;
     const float ax = __ldg(p1) - __ldg(p0), ay = __ldg(p1 + 1) - __ldg(p0 + 1), az = __ldg(p1 + 2) - __ldg(p0 + 2);
     const float bx = __ldg(p2) - __ldg(p0), by = __ldg(p2 + 1) - __ldg(p0 + 1), bz = __ldg(p2 + 2) - __ldg(p0 + 2);
-    const float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const float n[3] = { ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx };
+    const int se = normal_scale_exp(__ldg(extent_bits));
+    long long q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // a non-finite component (non-finite vertex) poisons the vertices of this face only, as in the reference;
+        // it is carried as the most negative value, which the finishing pass turns back into NaN
+        const double d = ldexp((double)n[k], se);
+        q[k] = (fabs(d) < 9.0e18) ? __double2ll_rn(d) : (long long)0x8000000000000000ull;
+    }
     const int idx[3] = { i0, i1, i2 };
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float *d = acc + 3 * (size_t)idx[k];
-        atomicAdd(d, nx); atomicAdd(d + 1, ny); atomicAdd(d + 2, nz);
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(acc + 3 * (size_t)idx[k]);
+        atomicAdd(d, (unsigned long long)q[0]); atomicAdd(d + 1, (unsigned long long)q[1]); atomicAdd(d + 2, (unsigned long long)q[2]);
     }
 }
 
-__global__ void __launch_bounds__(256) k_normalize_vertex_normals(float *acc, int V)
+__global__ void __launch_bounds__(256) k_normalize_vertex_normals(const long long *acc, const unsigned *extent_bits, int V,
+                                                                  float *v_nrm)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    float x = acc[3 * (size_t)v], y = acc[3 * (size_t)v + 1], z = acc[3 * (size_t)v + 2];
+    const int se = normal_scale_exp(__ldg(extent_bits));
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const long long q = acc[3 * (size_t)v + k];
+        // |sum| beyond 2^62 can only come from a poisoned (non-finite) contribution
+        c[k] = (q > -(1ll << 62) && q < (1ll << 62)) ? (float)ldexp((double)q, -se) : __int_as_float(0x7FC00000);
+    }
+    float x = c[0], y = c[1], z = c[2];
     const float sq = (x * x + y * y) + z * z;
     if (!(sq > 1e-20f)) { x = 0.0f; y = 0.0f; z = 1.0f; }
     const float n = sqrtf((x * x + y * y) + z * z);
     const float d = fmaxf(n, 1e-12f);
-    acc[3 * (size_t)v] = x / d; acc[3 * (size_t)v + 1] = y / d; acc[3 * (size_t)v + 2] = z / d;
+    v_nrm[3 * (size_t)v] = x / d; v_nrm[3 * (size_t)v + 1] = y / d; v_nrm[3 * (size_t)v + 2] = z / d;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -232,17 +277,25 @@ extern "C" int wr_vertex_normals(wr_ctx *ctx, const float *v_pos, int V, const i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
-    e = cudaMemsetAsync(v_nrm, 0, (size_t)V * 3 * sizeof(float), stream);
+    // scratch: [V,3] int64 fixed-point sums + the extent word
+    const size_t acc_bytes = wr_align256((size_t)V * 3 * sizeof(long long));
+    int rc = wr_scratch_reserve(ctx, acc_bytes + 256, stream);
+    if (rc != WR_OK) return rc;
+    ctx->clean_bytes = 0;
+    long long *acc = static_cast<long long *>(ctx->scratch);
+    unsigned *extent = reinterpret_cast<unsigned *>(static_cast<char *>(ctx->scratch) + acc_bytes);
+    e = cudaMemsetAsync(acc, 0, acc_bytes + 256, stream);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "memset normals");
+    k_vertex_extent<<<min(wr_div_up((long long)V * 3, 256 * 8), ctx->sm_count * 8), 256, 0, stream>>>(v_pos, (long long)V * 3, extent);
+    WR_CHECK_LAUNCH(ctx, "k_vertex_extent");
     if (F > 0) {
-        k_face_normals_scatter<<<wr_div_up(F, 256), 256, 0, stream>>>(v_pos, V, tri, F, v_nrm);
+        k_face_normals_scatter<<<wr_div_up(F, 256), 256, 0, stream>>>(v_pos, V, tri, F, acc, extent);
         WR_CHECK_LAUNCH(ctx, "k_face_normals_scatter");
     }
-    k_normalize_vertex_normals<<<wr_div_up(V, 256), 256, 0, stream>>>(v_nrm, V);
+    k_normalize_vertex_normals<<<wr_div_up(V, 256), 256, 0, stream>>>(acc, extent, V, v_nrm);
     WR_CHECK_LAUNCH(ctx, "k_normalize_vertex_normals");
     return WR_OK;
 }
-
 
 extern "C" int wr_vertex_tangents(wr_ctx *ctx, const float *v_pos, int V, const int32_t *tri, const float *v_tex, int Vt,
                                   const int32_t *tri_tex, int F, const float *v_nrm, float *v_tang, void *stream_)
