@@ -91,29 +91,39 @@ extern "C" void wr_ctx_destroy(wr_ctx *ctx)
         for (int i = 0; i <= WR_MAX_STAGES; ++i) cudaEventDestroy(ctx->marks[i]);
     if (ctx->scratch) {
         cudaSetDevice(ctx->device);
-        cudaFree(ctx->scratch);
+        cudaFree(ctx->scratch);   // synchronises: nothing of this context is in flight afterwards
     }
     free(ctx);
 }
 
-// Grow-only scratch.  Growth frees the old block with cudaFree, which waits for work in flight.
+// Grow-only scratch, stream-ordered: the old block is released with cudaFreeAsync and the new one comes from
+// cudaMallocAsync on the caller's stream, so growth neither synchronises the device (cudaFree would) nor races with
+// kernels of earlier calls that still read the old block (they precede the free in stream order).  A context is used
+// from one stream at a time (include/wr_b200.h).  Growth inside a stream capture is refused: the captured kernels
+// would hold pointers into a block the graph does not own -- warm the context up first (RenderGraph does).
 int wr_scratch_reserve(wr_ctx *ctx, size_t bytes, cudaStream_t stream)
 {
-    (void)stream;
     if (bytes <= ctx->scratch_bytes) return WR_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+        snprintf(ctx->last_error, sizeof(ctx->last_error),
+                 "scratch would have to grow (%zu -> %zu bytes) inside a stream capture", ctx->scratch_bytes, bytes);
+        return WR_ERR_UNSUPPORTED;
+    }
     ctx->clean_bytes = 0;
     if (ctx->scratch) {
-        cudaFree(ctx->scratch);
+        cudaError_t fe = cudaFreeAsync(ctx->scratch, stream);
+        if (fe != cudaSuccess) { cudaGetLastError(); cudaFree(ctx->scratch); }
         ctx->scratch = nullptr;
         ctx->scratch_bytes = 0;
     }
     const size_t want = bytes + bytes / 8;  // headroom so slightly larger calls do not reallocate
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, want);
+    cudaError_t e = cudaMallocAsync(&p, want, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        e = cudaMalloc(&p, bytes);
-        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaMalloc(scratch)");
+        e = cudaMallocAsync(&p, bytes, stream);
+        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaMallocAsync(scratch)");
         ctx->scratch_bytes = bytes;
     } else {
         ctx->scratch_bytes = want;

@@ -193,22 +193,25 @@ def _p2p_workspace(uv_h: int, uv_w: int, device: torch.device, group, slot: int 
     return ws
 
 
-_PRE_CACHE: Dict[int, tuple] = {}
+_PRE_CACHE: Dict[tuple, tuple] = {}
+_PRE_CACHE_SLOTS = 4
 
 
 def _uv_precompute_cached(ctx, mesh, uv_size: int):
-    """uv_precompute is replicated on every rank and depends on the mesh and atlas size only: keep the last one
-    per device while the mesh tensors are unchanged (same storage and version), like CameraProjection does."""
+    """uv_precompute is replicated on every rank and depends on the mesh and atlas size only: the last few
+    (device, mesh tensors, size) results are kept while the mesh tensors are unchanged (same storage and version;
+    the entry holds the tensors themselves, so their addresses cannot be recycled), like CameraProjection does."""
     from .uv import UVPrecomputeOutput, uv_precompute
     srcs = (mesh.v_pos, mesh.t_pos_idx, mesh.v_tex, mesh.t_tex_idx)
-    key = (int(uv_size),) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
-    slot = ctx.device.index
-    hit = _PRE_CACHE.get(slot)
-    if hit is None or hit[0] != key:
+    key = (ctx.device.index, int(uv_size)) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in srcs)
+    hit = _PRE_CACHE.pop(key, None)
+    if hit is None or any(a is not b for a, b in zip(hit[0], srcs)):
         pre = uv_precompute(ctx, mesh, uv_size, uv_size)
-        hit = (key, srcs, pre.uv_mask, pre.uv_pos)
-        _PRE_CACHE[slot] = hit
-    return UVPrecomputeOutput(height=uv_size, width=uv_size, uv_attr=mesh.texture, uv_mask=hit[2], uv_pos=hit[3])
+        hit = (srcs, pre.uv_mask, pre.uv_pos)
+    _PRE_CACHE[key] = hit                       # most recently used last
+    while len(_PRE_CACHE) > _PRE_CACHE_SLOTS:
+        _PRE_CACHE.pop(next(iter(_PRE_CACHE)))
+    return UVPrecomputeOutput(height=uv_size, width=uv_size, uv_attr=mesh.texture, uv_mask=hit[1], uv_pos=hit[2])
 
 
 def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_size: int, *, view_masks_local=None,
