@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
             const float cx = ((m[0] * ux + m[1] * uy) + m[2] * uz) + m[3];
             const float cy = ((m[4] * ux + m[5] * uy) + m[6] * uz) + m[7];
             const float cw = ((m[12] * ux + m[13] * uy) + m[14] * uz) + m[15];
-            const float gx = cx / cw, gy = cy / cw;  // uv.py:90, no w > 0 guard
+            // uv.py:90, no w > 0 guard.  x / 1 == x exactly: an orthographic view (w is exactly 1 for every texel)
+            // skips the two IEEE divisions, ~40 instructions of the ~210 per texel and view
+            const bool unit_w = cw == 1.0f;
+            const float gx = unit_w ? cx : cx / cw, gy = unit_w ? cy : cy / cw;
             const Bilinear t = make_bilinear(gx, gy, A.W, A.H);
             const float4 geo = sample4(reinterpret_cast<const float4 *>(A.geo_map) + v * npix, t, A.W, A.H);
             const float dx = geo.x - ux, dy = geo.y - uy, dz = geo.z - uz;
