@@ -11,6 +11,7 @@ import torch
 from PIL import Image
 
 import worldrenderer_b200 as wr
+from worldrenderer_b200 import synth
 from worldrenderer_b200 import _native, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -164,6 +165,21 @@ def test_no_cpu_path():
         wr.SmartPainter("cpu", "cuda")   # a caller of the path: needs a CUDA device like everything else
     with pytest.raises(NotImplementedError):
         wr.replace_mesh_texture_and_save()
+    # mesh-level kernels and the tangent-space helper refuse CPU tensors instead of falling back to torch ops
+    v, f = synth.icosphere(2, 0.5)
+    vt, ft = synth.cell_atlas_uv(f.shape[0])
+    m = wr.TexturedMesh(v_pos=torch.tensor(v, dtype=torch.float32), t_pos_idx=torch.tensor(f),
+                        v_tex=torch.tensor(vt, dtype=torch.float32), t_tex_idx=torch.tensor(ft))
+    m.set_stitched_mesh(m.v_pos, m.t_pos_idx)
+    with pytest.raises(RuntimeError):
+        m.v_nrm
+    with pytest.raises(RuntimeError):
+        m.v_tang
+    z = torch.zeros(6, 4, 4, 3)
+    with pytest.raises(RuntimeError):
+        wr.view_normals_to_tangent_space(z, wr.RenderOutput(normal=z, tangent=z))
+    with pytest.raises(ValueError):
+        wr.view_normals_to_tangent_space(z, wr.RenderOutput(normal=z))
 
 
 def _declared_functions():

@@ -1162,7 +1162,6 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
 #ifndef WR_MV
 #define WR_MV 1
 #endif
-    const int Bp = (B + 1) & ~1;
     const bool use_mv = WR_MV && src.mvp && !tri_ranges && W <= 2048 && H <= 2048 && F > 0 && V > 0 &&
                         (long long)F * 4 > (long long)H * W && (long long)V * B < (1ll << 31);
     const size_t sv_bytes = use_mv ? wr_align256((size_t)V * B * sizeof(int2))
