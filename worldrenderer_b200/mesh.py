@@ -159,11 +159,14 @@ class TexturedMesh:
         return out
 
     def to(self, device: Optional[str] = None):
+        moved = {}   # tensors that alias each other (an unstitched mesh shares v_pos / t_pos_idx) keep doing so
         for name in ("v_pos", "t_pos_idx", "v_tex", "t_tex_idx", "texture", "_stitched_v_pos",
                      "_stitched_t_pos_idx", "_v_nrm", "_v_tang"):
             val = getattr(self, name)
             if val is not None:
-                setattr(self, name, val.to(device))
+                if id(val) not in moved:
+                    moved[id(val)] = val.to(device)
+                setattr(self, name, moved[id(val)])
         self._i32_cache.clear()
 
 
