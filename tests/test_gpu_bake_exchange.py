@@ -54,6 +54,7 @@ def test_p2p_exchange_emulated_ranks(wr_ctx, world, Hu, Wu, with_old):
             a.accum[r], a.out_attr[r], a.out_valid[r] = _native.ptr(acc[r]), _native.ptr(attr[r]), _native.ptr(valid[r])
         a.old_attr = _native.ptr(old) if old is not None else None
         a.world, a.rank, a.Hu, a.Wu = world, rank, Hu, Wu
+        a.max_blocks = 0 if rank % 2 == 0 else 3   # a bounded grid (BakePipeline) must cover the same texels
         c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()), "wr_uv_reduce_finalize_p2p")
     torch.cuda.synchronize()
     total = torch.stack(acc).sum(0)
@@ -122,12 +123,15 @@ def test_multicast_exchange_single_rank_window(wr_ctx):
         a.old_attr = _native.ptr(old)
         a.world, a.rank, a.Hu, a.Wu = 1, 0, Hu, Wu
         c = wr_ctx.ctx
-        torch.cuda.synchronize()
-        c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()), "wr_uv_reduce_finalize_p2p(mc)")
-        torch.cuda.synchronize()
         want_attr, want_any = uv_finalize(wr_ctx, accum.clone(), old)
-        np.testing.assert_array_equal(valid.cpu().numpy().astype(bool), want_any.cpu().numpy())
-        np.testing.assert_allclose(attr.cpu().numpy(), want_attr.cpu().numpy(), rtol=1e-5, atol=1e-6)
+        for max_blocks in (0, 37):   # the stand-alone kernel, then the light bounded one BakePipeline launches
+            attr.fill_(-3.0); valid.fill_(7)
+            a.max_blocks = max_blocks
+            torch.cuda.synchronize()
+            c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()), "wr_uv_reduce_finalize_p2p(mc)")
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(valid.cpu().numpy().astype(bool), want_any.cpu().numpy())
+            np.testing.assert_allclose(attr.cpu().numpy(), want_attr.cpu().numpy(), rtol=1e-5, atol=1e-6)
     finally:
         if created:
             dist.destroy_process_group()

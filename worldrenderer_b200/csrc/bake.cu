@@ -513,24 +513,30 @@ __device__ __forceinline__ void multimem_st_f32(float *mc_addr, float v)
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_uv_reduce_finalize_mc(wr_p2p_reduce_args A, long long ntex, long long blk_lo,
-                                                               long long blk_hi)
+// T threads per block, 4 T texels per block iteration.  T = 64 with one block per SM (4 K registers and 5 KB of
+// shared memory per SM) is what runs: the exchange is bound by the NVSwitch round trips, not by the SMs, and a small
+// footprint matters when it runs under another bake's view passes, whose kernels need the whole register file for
+// their own occupancy.
+template <int T>
+__global__ void __launch_bounds__(T) k_uv_reduce_finalize_mc(wr_p2p_reduce_args A, long long ntex, long long blk_lo,
+                                                             long long blk_hi)
 {
-    __shared__ float4 s_sum[kP2PTexelsPerBlock * 5 / 4];
+    constexpr int kTexels = 4 * T;
+    __shared__ float4 s_sum[kTexels * 5 / 4];
     for (long long blk = blk_lo + blockIdx.x; blk < blk_hi; blk += gridDim.x) {
-        const long long t0 = blk * kP2PTexelsPerBlock;
-        const long long nt = min((long long)kP2PTexelsPerBlock, ntex - t0);
+        const long long t0 = blk * kTexels;
+        const long long nt = min((long long)kTexels, ntex - t0);
         const int nchunks = (int)(nt * 5 / 4);
         {   // all five 16-byte reductions of a thread are issued before the first result is consumed
             float4 v[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                const int j = threadIdx.x + k * 256;
+                const int j = threadIdx.x + k * T;
                 if (j < nchunks) v[k] = multimem_ld_reduce_add_f32x4(A.mc_accum + 5 * t0 + 4 * (long long)j);
             }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                const int j = threadIdx.x + k * 256;
+                const int j = threadIdx.x + k * T;
                 if (j < nchunks) s_sum[j] = v[k];
             }
         }
@@ -707,7 +713,12 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaSetDevice");
-    const long long nblk = (ntex + kP2PTexelsPerBlock - 1) / kP2PTexelsPerBlock;
+    // The multicast exchange always runs the light instantiation (64 threads, 256 texels per iteration, one block per
+    // SM): measured on 8 x B200 at 4096^2 it is as fast alone as 256-thread blocks (0.585 vs 0.596 ms) and costs the
+    // view passes of a concurrent bake 0.16 ms instead of 0.42 ms (tools/bake_pipeline_probe.py).
+    const bool light = multicast;
+    const long long tpb = light ? 256 : kP2PTexelsPerBlock;
+    const long long nblk = (ntex + tpb - 1) / tpb;
     const long long blk_lo = nblk * A.rank / A.world, blk_hi = nblk * (A.rank + 1) / A.world;
     if (blk_hi > blk_lo) {
         // peer loads want many blocks in flight (8 per SM: 0.52 ms against 0.82 ms with one, 2 x B200, 4096^2); the
@@ -717,7 +728,8 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
         wr_stage_begin(ctx);
         if (multicast) {
             wr_stage(ctx, stream, "k_uv_reduce_finalize_mc");
-            k_uv_reduce_finalize_mc<<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            if (light) k_uv_reduce_finalize_mc<64><<<grid, 64, 0, stream>>>(A, ntex, blk_lo, blk_hi);
+            else k_uv_reduce_finalize_mc<256><<<grid, 256, 0, stream>>>(A, ntex, blk_lo, blk_hi);
             WR_CHECK_LAUNCH(ctx, "k_uv_reduce_finalize_mc");
         } else {
             wr_stage(ctx, stream, "k_uv_reduce_finalize_p2p");
