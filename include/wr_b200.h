@@ -201,6 +201,9 @@ typedef struct wr_unproject_args {
     const float *old_attr;    /* [Hu,Wu,3] existing texture */
     float *out_attr;          /* [Hu,Wu,3] */
     uint8_t *out_valid_any;   /* [Hu,Wu] */
+    /* Texel range [tex_lo, tex_hi) of the flattened atlas this call covers; tex_hi == 0 means all of it.  A multi-GPU
+       bake unprojects its atlas chunk by chunk so that the exchange of a finished chunk runs under the next one. */
+    long long tex_lo, tex_hi;
 } wr_unproject_args;
 
 int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void *stream);
@@ -234,6 +237,9 @@ typedef struct wr_p2p_reduce_args {
        kernel is bound by NVLink, not by the SMs: a pipelined bake (parallel.BakePipeline) runs it with one or two
        blocks per SM so that the next bake's view passes keep the rest of the GPU. */
     int max_blocks;
+    /* Texel range [tex_lo, tex_hi) to exchange (each rank owns 1/N of it); tex_hi == 0 means the whole atlas.
+       tex_lo must be a multiple of 1024. */
+    long long tex_lo, tex_hi;
 } wr_p2p_reduce_args;
 int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *args, void *stream);
 

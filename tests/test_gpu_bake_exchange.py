@@ -86,6 +86,36 @@ def test_p2p_exchange_rejects_bad_arguments(wr_ctx):
     assert _native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()) != 0
 
 
+@pytest.mark.parametrize("world", [2, 8])
+def test_p2p_exchange_in_chunks(wr_ctx, world):
+    """The atlas exchanged chunk by chunk (tex_lo / tex_hi, what sharded_bake(chunks=...) issues): chunks on 1024-texel
+    boundaries, the last one ragged, every rank owning 1/N of each chunk -- same atlas as one exchange."""
+    dev = wr_ctx.device
+    Hu, Wu = 120, 172   # 20640 texels: chunks of 7168 texels -> 7168, 7168, 6304
+    acc = _accumulators(world, Hu, Wu, dev, seed=77)
+    old = torch.rand((Hu, Wu, 3), device=dev)
+    attr = [torch.full((Hu, Wu, 3), -7.0, device=dev) for _ in range(world)]
+    valid = [torch.full((Hu, Wu), 9, dtype=torch.uint8, device=dev) for _ in range(world)]
+    c = wr_ctx.ctx
+    ntex, step = Hu * Wu, 7168
+    for lo in range(0, ntex, step):
+        for rank in range(world):
+            a = _native.P2PReduceArgs()
+            for r in range(world):
+                a.accum[r], a.out_attr[r], a.out_valid[r] = _native.ptr(acc[r]), _native.ptr(attr[r]), _native.ptr(valid[r])
+            a.old_attr = _native.ptr(old)
+            a.world, a.rank, a.Hu, a.Wu = world, rank, Hu, Wu
+            a.tex_lo, a.tex_hi, a.max_blocks = lo, min(lo + step, ntex), 2
+            c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()), "wr_uv_reduce_finalize_p2p")
+    torch.cuda.synchronize()
+    want_attr, want_any = uv_finalize(wr_ctx, torch.stack(acc).sum(0).contiguous(), old)
+    for r in range(world):
+        np.testing.assert_array_equal(valid[r].cpu().numpy().astype(bool), want_any.cpu().numpy())
+        np.testing.assert_allclose(attr[r].cpu().numpy(), want_attr.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    a.tex_lo = 512   # not on a block boundary
+    assert _native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()) != 0
+
+
 def test_multicast_exchange_single_rank_window(wr_ctx):
     """k_uv_reduce_finalize_mc through a real multicast window (world = 1)."""
     import torch.distributed as dist

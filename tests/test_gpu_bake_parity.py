@@ -139,6 +139,23 @@ def test_accumulate_then_finalize_equals_fused(wr_ctx):
     torch.testing.assert_close(out, full, rtol=1e-5, atol=1e-6)
 
 
+def test_unprojection_in_texel_ranges_equals_one_pass(wr_ctx):
+    """wr_uv_unproject over texel ranges (what the chunked multi-GPU bake issues) fills the same accumulators."""
+    from worldrenderer_b200.uv import fused_unproject, fused_view_maps
+    mesh, cam, images = _setup(wr_ctx.device)
+    pre = wr.uv_precompute(wr_ctx, mesh, 128, 128)
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    kw = dict(aoi_cos_thresh=0.2, depth_grad_thresh=0.1, alpha=3.0, accumulate_only=True)
+    _, geo, att = fused_view_maps(wr_ctx, mesh, cam, img, 96, 96, 5)
+    _, _, full, _, _ = fused_unproject(wr_ctx, pre, cam, 96, 96, geo, att, **kw)
+    part = torch.full_like(full, float("nan"))
+    for lo, hi in [(0, 5000), (5000, 5001), (5001, 16384)]:
+        fused_unproject(wr_ctx, pre, cam, 96, 96, geo, att, accum=part, add_to_accum=False, tex_range=(lo, hi), **kw)
+    assert torch.equal(part, full)
+    with pytest.raises(RuntimeError):
+        fused_unproject(wr_ctx, pre, cam, 96, 96, geo, att, accum=part, add_to_accum=False, tex_range=(10, 5), **kw)
+
+
 def test_unsupported_options_raise(wr_ctx):
     mesh, cam, images = _setup(wr_ctx.device)
     proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")

@@ -65,6 +65,7 @@ class UnprojectArgs(ctypes.Structure):
         ("uv_aoi_cos", ctypes.c_void_p), ("uv_depth_grad", ctypes.c_void_p), ("uv_attr_proj", ctypes.c_void_p),
         ("uv_mask_proj", ctypes.c_void_p), ("uv_valid", ctypes.c_void_p), ("uv_weight", ctypes.c_void_p),
         ("old_attr", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_valid_any", ctypes.c_void_p),
+        ("tex_lo", ctypes.c_longlong), ("tex_hi", ctypes.c_longlong),
     ]
 
 
@@ -78,6 +79,7 @@ class P2PReduceArgs(ctypes.Structure):
         ("world", ctypes.c_int), ("rank", ctypes.c_int), ("Hu", ctypes.c_int), ("Wu", ctypes.c_int),
         ("mc_accum", ctypes.c_void_p), ("mc_attr", ctypes.c_void_p), ("mc_valid", ctypes.c_void_p),
         ("max_blocks", ctypes.c_int),
+        ("tex_lo", ctypes.c_longlong), ("tex_hi", ctypes.c_longlong),
     ]
 
 

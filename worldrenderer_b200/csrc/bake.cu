@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
     __syncthreads();
 
     const long long ntex = (long long)A.Hu * A.Wu;
-    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= ntex) return;
+    const long long o = A.tex_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= (A.tex_hi ? A.tex_hi : ntex)) return;
     const bool inside = A.uv_mask[o] != 0;
     float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f;
     int nvalid = 0;
@@ -429,8 +429,8 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
 {
     __shared__ float4 s_sum[kP2PTexelsPerBlock * 5 / 4];  // 1280 float4 = 20 KB
     for (long long blk = blk_lo + blockIdx.x; blk < blk_hi; blk += gridDim.x) {
-        const long long t0 = blk * kP2PTexelsPerBlock;
-        const long long nt = min((long long)kP2PTexelsPerBlock, ntex - t0);  // multiple of 4
+        const long long t0 = A.tex_lo + blk * kP2PTexelsPerBlock;
+        const long long nt = min((long long)kP2PTexelsPerBlock, ntex - t0);  // multiple of 4 (ntex: end of the range)
         const int nchunks = (int)(nt * 5 / 4);
         // per chunk: one 16-byte load from every rank in flight together, starting at the next rank so that the
         // ranks do not all pull from rank 0 at the same moment.  The summation order (rank+1, rank+2, ...) is a
@@ -524,8 +524,8 @@ __global__ void __launch_bounds__(T) k_uv_reduce_finalize_mc(wr_p2p_reduce_args 
     constexpr int kTexels = 4 * T;
     __shared__ float4 s_sum[kTexels * 5 / 4];
     for (long long blk = blk_lo + blockIdx.x; blk < blk_hi; blk += gridDim.x) {
-        const long long t0 = blk * kTexels;
-        const long long nt = min((long long)kTexels, ntex - t0);
+        const long long t0 = A.tex_lo + blk * kTexels;
+        const long long nt = min((long long)kTexels, ntex - t0);   // ntex: end of the range
         const int nchunks = (int)(nt * 5 / 4);
         {   // all five 16-byte reductions of a thread are issued before the first result is consumed
             float4 v[5];
@@ -674,7 +674,8 @@ extern "C" int wr_uv_unproject(wr_ctx *ctx, const wr_unproject_args *args, void 
     wr_stage(ctx, stream, "k_uv_unproject");
     const bool heavy = A.uv_pos_ndc || A.uv_pos_proj || A.uv_pos_error || A.uv_attr_proj || A.uv_mask_proj || A.uv_valid ||
                        A.uv_weight;
-    const dim3 grid(wr_div_up(ntex, 256)), block(256);
+    if (A.tex_lo < 0 || A.tex_hi < 0 || A.tex_hi > ntex || (A.tex_hi && A.tex_lo >= A.tex_hi)) return WR_ERR_INVALID_ARGUMENT;
+    const dim3 grid(wr_div_up((A.tex_hi ? A.tex_hi : ntex) - A.tex_lo, 256)), block(256);
     if (heavy) wr_launch_s(k_uv_unproject<1>, grid, block, smem, stream, !ctx->profiling, A);
     else if (materialise) wr_launch_s(k_uv_unproject<2>, grid, block, smem, stream, !ctx->profiling, A);
     else wr_launch_s(k_uv_unproject<0>, grid, block, smem, stream, !ctx->profiling, A);
@@ -702,8 +703,12 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
     const wr_p2p_reduce_args &A = *args;
     if (A.world < 1 || A.world > WR_MAX_P2P_RANKS || A.rank < 0 || A.rank >= A.world || A.Hu <= 0 || A.Wu <= 0)
         return WR_ERR_INVALID_ARGUMENT;
-    const long long ntex = (long long)A.Hu * A.Wu;
-    if (ntex % 4 != 0) return WR_ERR_UNSUPPORTED;
+    const long long natlas = (long long)A.Hu * A.Wu;
+    if (natlas % 4 != 0) return WR_ERR_UNSUPPORTED;
+    if (A.tex_lo < 0 || A.tex_hi < 0 || A.tex_hi > natlas || (A.tex_lo & 1023) || (A.tex_hi & 3) ||
+        (A.tex_hi && A.tex_lo >= A.tex_hi))
+        return WR_ERR_INVALID_ARGUMENT;
+    const long long ntex = A.tex_hi ? A.tex_hi : natlas;   // end of the exchanged range (the kernels' `ntex`)
     const bool multicast = A.mc_accum && A.mc_attr && A.mc_valid;
     for (int r = 0; r < A.world && !multicast; ++r) {
         if (!A.accum[r] || !A.out_attr[r] || !A.out_valid[r]) return WR_ERR_INVALID_ARGUMENT;
@@ -718,7 +723,7 @@ extern "C" int wr_uv_reduce_finalize_p2p(wr_ctx *ctx, const wr_p2p_reduce_args *
     // view passes of a concurrent bake 0.16 ms instead of 0.42 ms (tools/bake_pipeline_probe.py).
     const bool light = multicast;
     const long long tpb = light ? 256 : kP2PTexelsPerBlock;
-    const long long nblk = (ntex + tpb - 1) / tpb;
+    const long long nblk = (ntex - A.tex_lo + tpb - 1) / tpb;   // blocks of the range, counted from tex_lo
     const long long blk_lo = nblk * A.rank / A.world, blk_hi = nblk * (A.rank + 1) / A.world;
     if (blk_hi > blk_lo) {
         // peer loads want many blocks in flight (8 per SM: 0.52 ms against 0.82 ms with one, 2 x B200, 4096^2); the

@@ -127,7 +127,7 @@ class P2PBakeWorkspace:
         self.hdl.barrier(channel=channel)  # device-side, ordered on the current stream
 
     def reduce_finalize(self, ctx, old_attr: Optional[torch.Tensor], multicast: Optional[bool] = None,
-                        max_blocks: int = 0):
+                        max_blocks: int = 0, tex_range: Optional[Tuple[int, int]] = None, last: bool = True):
         """multicast: True / False force the NVSwitch multicast (multimem) or the peer load / store kernel; None
         picks multicast from 4 ranks up when the window exists (measured on 8 x B200, 4096^2 atlas: multicast
         0.64 ms, peer 1.19 ms, NCCL all_reduce + finalize 1.09 ms; on 2 ranks peer 0.52 ms, multicast 0.79 ms)."""
@@ -150,11 +150,14 @@ class P2PBakeWorkspace:
             a.old_attr = _native.ptr(old)
         a.world, a.rank, a.Hu, a.Wu = self.world, self.rank, self.uv_h, self.uv_w
         a.max_blocks = int(max_blocks)
-        self.barrier(0)  # every rank's accumulators are complete
+        if tex_range is not None:   # one chunk of the atlas: every rank owns 1/N of it
+            a.tex_lo, a.tex_hi = int(tex_range[0]), int(tex_range[1])
+        self.barrier(0)  # every rank's accumulators (of this chunk) are complete
         c = ctx.ctx
         c.check(_native.lib().wr_uv_reduce_finalize_p2p(c.handle, ctypes.byref(a), c.stream()),
                 "wr_uv_reduce_finalize_p2p")
-        self.barrier(1)  # every rank's share of this atlas has landed
+        if last:
+            self.barrier(1)  # every rank's share of this atlas has landed
         del old
         return self.attr, self.valid.view(torch.bool)
 
@@ -219,7 +222,7 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
                  depth_grad_threshold: Optional[float] = 0.1, uv_exp_blend_alpha: float = 6.0,
                  uv_exp_blend_view_weight_local=None, group=None, exchange: str = "auto",
                  uv_padding: bool = False, poisson_blending: bool = False, pb_solver=None, pb_num_iters: int = 1000,
-                 pb_keep_original_border: bool = True, from_scratch: bool = False, _slot: int = 0,
+                 pb_keep_original_border: bool = True, from_scratch: bool = False, chunks: int = 4, _slot: int = 0,
                  _exchange_stream: Optional["torch.cuda.Stream"] = None, _exchange_blocks: int = 0):
     """Config E: this rank holds `cam_local` / `images_local` (its share of the views, possibly none);
     the mesh is replicated.  Returns (atlas [uv,uv,3], valid_any [uv,uv] bool), identical on all ranks.
@@ -228,6 +231,9 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
               "nccl" -- all_reduce(SUM) of the accumulators, then wr_uv_finalize on every rank;
               "auto" -- p2p when symmetric memory is available for the group, else nccl.
     With "p2p" / "auto" the returned tensors are views of the workspace: valid until the next bake of that size.
+
+    chunks: with peer memory the atlas is unprojected and exchanged in this many chunks, the exchange of chunk k on a
+    side stream under the unprojection of chunk k + 1 (1 = unproject everything, then exchange).
 
     uv_padding / poisson_blending: the post-processing tail of uv_blend (uv.py:426-461) applied to the exchanged
     atlas.  It is deterministic and cheap next to the exchange, so every rank runs it on its own copy (no second
@@ -241,34 +247,88 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
         raise RuntimeError("exchange='p2p' requested but peer memory is not available for this process group")
     n_local = cam_local.mvp_mtx.shape[0]
     accum = ws.accum if ws is not None else None
+    geo = att = None
     if n_local > 0:
         H, W = int(images_local.shape[1]), int(images_local.shape[2])
         _, geo, att = fused_view_maps(ctx, mesh, cam_local, images_local, H, W, int(depth_grad_dilation))
-        _, _, accum, _, _ = fused_unproject(
-            ctx, pre, cam_local, H, W, geo, att, view_masks=view_masks_local, aoi_cos_thresh=aoi_cos_valid_threshold,
-            depth_grad_thresh=depth_grad_threshold, alpha=uv_exp_blend_alpha,
-            view_weight=uv_exp_blend_view_weight_local, accumulate_only=True, accum=accum, add_to_accum=False)
-    elif accum is not None:
-        accum.zero_()
-    else:
-        accum = torch.zeros((uv_size, uv_size, 5), dtype=torch.float32, device=ctx.device)
+
+    def unproject(tex_range=None):
+        nonlocal accum
+        if n_local > 0:
+            _, _, accum, _, _ = fused_unproject(
+                ctx, pre, cam_local, H, W, geo, att, view_masks=view_masks_local, aoi_cos_thresh=aoi_cos_valid_threshold,
+                depth_grad_thresh=depth_grad_threshold, alpha=uv_exp_blend_alpha,
+                view_weight=uv_exp_blend_view_weight_local, accumulate_only=True, accum=accum, add_to_accum=False,
+                tex_range=tex_range)
+
+    cur = torch.cuda.current_stream(ctx.device)
     xs = _exchange_stream
-    if xs is not None:  # BakePipeline: the exchange (and everything after it) runs on its own stream
-        xs.wait_stream(torch.cuda.current_stream(ctx.device))
-        accum.record_stream(xs)
-    with torch.cuda.stream(xs) if xs is not None else contextlib.nullcontext():
-        if ws is not None:
-            atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr, max_blocks=_exchange_blocks)
+    ntex = uv_size * uv_size
+    nchunks = max(1, min(int(chunks), ntex // (1 << 16))) if ws is not None else 1
+    if nchunks > 1:
+        # The atlas in chunks: the exchange of a finished chunk runs on the side stream under the unprojection of the
+        # next one (every rank runs the same chunk loop: the barriers inside reduce_finalize pair up).
+        if n_local == 0:
+            accum.zero_()
+        side = xs if xs is not None else _side_stream(ctx.device)
+        # Chunk sizes fall linearly (K : K-1 : ... : 1): unprojection and exchange run at about the same rate, so what
+        # stays exposed is the exchange of the LAST chunk -- make that one small.  Boundaries on 1024 texels (the
+        # exchange kernels' blocks).
+        total_w = nchunks * (nchunks + 1) // 2
+        bounds, lo = [], 0
+        for k in range(nchunks):
+            hi = ntex if k == nchunks - 1 else min(ntex, (lo + ntex * (nchunks - k) // total_w + 1023) & ~1023)
+            if hi > lo:
+                bounds.append((lo, hi))
+            lo = hi
+        # a small exchange grid leaves the SMs to the unprojection: one block per SM for the multicast kernel (its best
+        # anyway), two for the peer-load kernel (it needs more loads in flight)
+        sms = torch.cuda.get_device_properties(ctx.device).multi_processor_count
+        blocks = _exchange_blocks or sms * (1 if (ws.mc_ptr and ws.world >= 4) else 2)
+        for k, rng in enumerate(bounds):
+            unproject(rng)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr, max_blocks=blocks, tex_range=rng,
+                                                      last=k == len(bounds) - 1)
+        if xs is None:
+            cur.wait_stream(side)
+        if xs is not None:
+            return atlas, valid_any
+    else:
+        if n_local > 0:
+            unproject()
+        elif accum is not None:
+            accum.zero_()
         else:
-            all_reduce_accumulators(accum, group)
-            atlas, valid_any = uv_finalize(ctx, accum, pre.uv_attr)
-    if xs is not None:
-        return atlas, valid_any
+            accum = torch.zeros((uv_size, uv_size, 5), dtype=torch.float32, device=ctx.device)
+        if xs is not None:  # BakePipeline: the exchange (and everything after it) runs on its own stream
+            xs.wait_stream(cur)
+            accum.record_stream(xs)
+        with torch.cuda.stream(xs) if xs is not None else contextlib.nullcontext():
+            if ws is not None:
+                atlas, valid_any = ws.reduce_finalize(ctx, pre.uv_attr, max_blocks=_exchange_blocks)
+            else:
+                all_reduce_accumulators(accum, group)
+                atlas, valid_any = uv_finalize(ctx, accum, pre.uv_attr)
+        if xs is not None:
+            return atlas, valid_any
     if uv_padding or poisson_blending:
         atlas = atlas_postprocess(None, atlas, valid_any, pre, do_uv_padding=uv_padding, pad_unseen_area=from_scratch,
                                   poisson_blending=poisson_blending, pb_solver=pb_solver, pb_num_iters=pb_num_iters,
                                   pb_keep_original_border=pb_keep_original_border)
     return atlas, valid_any
+
+
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """High-priority stream for the exchange chunks of a single sharded_bake (one per device)."""
+    s = _SIDE_STREAMS.get(device.index)
+    if s is None:
+        s = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device, priority=-1)
+    return s
 
 
 class BakeTicket:

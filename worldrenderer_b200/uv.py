@@ -394,9 +394,11 @@ def fused_view_maps(ctx, mesh, cam, images, H, W, dilation):
 def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, geo, att, view_masks=None, *,
                     pos_error_eps=1e-3, aoi_cos_thresh=0.1, mask_thresh=0.9, depth_grad_thresh=None,
                     first_view_dominate=False, alpha=1.0, view_weight=None, want_per_view=False,
-                    accumulate_only=False, accum: Optional[torch.Tensor] = None, add_to_accum: bool = True):
+                    accumulate_only=False, accum: Optional[torch.Tensor] = None, add_to_accum: bool = True,
+                    tex_range: Optional[tuple] = None):
     """One wr_uv_unproject launch.  Returns (attr_blend, valid_any, accum, uv_depth_grad, uv_aoi_cos).
-    With accumulate_only, a given `accum` is added to (add_to_accum=True) or overwritten (False)."""
+    With accumulate_only, a given `accum` is added to (add_to_accum=True) or overwritten (False).
+    tex_range = (lo, hi): only these texels of the flattened atlas (the multi-GPU bake works chunk by chunk)."""
     dev = ctx.device
     uv_pos = _f32c(pre.uv_pos)
     uv_mask = pre.uv_mask.contiguous().view(torch.uint8)
@@ -445,6 +447,8 @@ def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, g
         out_attr = torch.empty((Hu, Wu, 3), dtype=torch.float32, device=dev)
         out_any = torch.empty((Hu, Wu), dtype=torch.uint8, device=dev)
         a.out_attr, a.out_valid_any = _native.ptr(out_attr), _native.ptr(out_any)
+    if tex_range is not None:
+        a.tex_lo, a.tex_hi = int(tex_range[0]), int(tex_range[1])
     c = ctx.ctx
     c.check(_native.lib().wr_uv_unproject(c.handle, ctypes.byref(a), c.stream()), "wr_uv_unproject")
     del keep
