@@ -400,6 +400,44 @@ def run_ours(args):
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = world * N_VIEWS * Ke / float(e2e_dt.item())
 
+    # ---- what the box's PCIe path gives all ranks at once: the same pinned buffers, copies only -------
+    # (the e2e loop above is bound by its read-back; this is the ceiling it is compared with: every rank moves the
+    # step's 102.6 MB of maps to the host and the 30 MB mesh to the device, concurrently, nothing else running)
+    pcie = None
+    try:
+        src = {k: torch.empty(t.shape, dtype=t.dtype, device=dev) for k, t in host_out.items()}
+
+        def copies(n):
+            for _ in range(n):
+                with torch.cuda.stream(s_d2h):
+                    for name, dst in host_out.items():
+                        dst.copy_(src[name], non_blocking=True)
+                with torch.cuda.stream(s_h2d):
+                    dev_in[0]["v"].copy_(v_host, non_blocking=True)
+                    dev_in[0]["f"].copy_(f_host, non_blocking=True)
+            torch.cuda.synchronize()
+
+        copies(3)
+        barrier()
+        reps_c = 30
+        t0 = time.perf_counter()
+        copies(reps_c)
+        barrier()
+        c_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(c_dt, op=dist.ReduceOp.MAX)
+        c_dt = float(c_dt.item())
+        pcie = {"d2h_gbs_all_ranks": world * reps_c * d2h / c_dt / 1e9,
+                "h2d_gbs_all_ranks": world * reps_c * (h2d - 2 * mvp_host.numel() * 4) / c_dt / 1e9,
+                "steps_per_s_all_ranks_copies_only": world * reps_c / c_dt,
+                "e2e_d2h_gbs_all_ranks": e2e_value / N_VIEWS * d2h / 1e9,
+                "e2e_frac_of_copy_ceiling": (e2e_value / N_VIEWS) / (world * reps_c / c_dt),
+                "what": f"{world} rank(s) at once, {reps_c} x (the step's four maps device -> pinned host on one "
+                        "stream + the step's mesh pinned host -> device on another), wall clock, max over ranks"}
+        del src
+    except Exception as exc:  # a measurement aid: never let it take the bench line down
+        pcie = {"error": repr(exc)}
+
     # ---- bake (config C) and config A, rank 0 ------------------------------------------------------
     bake, config_a = None, None
     if rank == 0 and not args.no_bake:
@@ -448,7 +486,8 @@ def run_ours(args):
                     "steps": Ke, "what": "render() per step on a mesh uploaded from pinned host memory (positions f32 + "
                                          "faces i64 + cameras), vertex normals, 6 views, all four maps copied back to "
                                          "pinned host memory; steps are software-pipelined over three streams "
-                                         "(upload k+1 | render k | read back k-1)"},
+                                         "(upload k+1 | render k | read back k-1)",
+                    "pcie_ceiling": pcie},
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "clocks": sampler.summary(),
@@ -776,6 +815,17 @@ def bench_bake(ctx, dev, flush_buf):
         unproj_ms = timed(lambda: fused_unproject(ctx, pre, cam, H, W, geo, att, aoi_cos_thresh=0.2,
                                                   depth_grad_thresh=0.1, alpha=3.0,
                                                   view_weight=torch.ones(N_VIEWS, device=dev)))
+        # uv_precompute (uv.py:24-53) on its own: UV-space raster of the 50k faces + position interpolation.
+        # CameraProjection caches it per (mesh, size), so it is outside ms_per_uv_bake_end_to_end after the first call.
+        pre_ms = {str(s_): timed(lambda: wr.uv_precompute(ctx, mesh, s_, s_), reps=10) for s_ in (1024, 4096)}
+        # the same CameraProjection call replayed from a CUDA graph (wr.BakeGraph): no launch gaps
+        graph_ms = None
+        try:
+            bg = wr.BakeGraph(proj, images, mesh, cam, **kw)
+            graph_ms = timed(bg.replay)
+            del bg
+        except Exception as exc:
+            graph_ms = repr(exc)
         # the reference's default tail (uv.py:426-461): seam padding, and Poisson blending with 1000 sweeps
         proj_pb = wr.CameraProjection("torch-cuda", None, str(dev), "cuda")
         proj_pb.ctx = ctx
@@ -786,7 +836,8 @@ def bench_bake(ctx, dev, flush_buf):
     peak, _ = peaks()
     bytes_unproj = 32 * N_VIEWS * H * W + 38 * uv * uv
     return {"workload": "config C: 50k-face icosphere, 6 x 768^2 images -> 1024^2 atlas, validity + cosine^3 weights",
-            "ms_per_uv_bake_end_to_end": e2e_ms, "ms_unprojection_only": unproj_ms,
+            "ms_per_uv_bake_end_to_end": e2e_ms, "ms_per_uv_bake_graph_replay": graph_ms,
+            "ms_unprojection_only": unproj_ms, "ms_uv_precompute": pre_ms,
             "ms_per_uv_bake_with_seam_padding": pad_ms,
             "ms_per_uv_bake_with_padding_and_poisson_1000_sweeps": pb_ms,
             "unprojection_algorithmic_bytes": bytes_unproj,

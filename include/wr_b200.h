@@ -151,6 +151,10 @@ typedef struct wr_render_args {
     float *out_attr;          /* [B,H,W,TC] */
     int32_t *out_tri_id;      /* [B,H,W] */
     float *out_rast;          /* [B,H,W,4] nvdiffrast layout */
+    /* cudaEvent_t or NULL: recorded on the stream once the raster passes are launched, before the shading pass.  A
+       caller that renders groups of views on several streams (graph.RenderGraph(view_lanes, stagger)) makes group
+       k + 1 wait for it, so that its issue-bound raster passes run next to the store-bound shading pass of group k. */
+    void *raster_done_event;
 } wr_render_args;
 
 int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream);

@@ -43,13 +43,16 @@ def test_graph_replay_equals_eager(wr_ctx, lanes):
     _same(outs[0], want)
 
 
-@pytest.mark.parametrize("view_lanes", [2, 3, 4])
-def test_view_lanes_equal_eager(wr_ctx, view_lanes):
-    """One job, its views split over concurrent lanes that render into slices of the job's outputs."""
+@pytest.mark.parametrize("stagger", [False, True])
+@pytest.mark.parametrize("view_lanes", [2, 3, 4, 6])
+def test_view_lanes_equal_eager(wr_ctx, view_lanes, stagger):
+    """One job, its views split over concurrent lanes that render into slices of the job's outputs; staggered: group
+    k + 1 waits for the raster-done event of group k (wr_render_args.raster_done_event)."""
     dev = wr_ctx.device
     cam = cases.canonical_cameras(device=dev)
     meshes = [_mesh(*cases.terrain_mesh(96, 64, seed=1), dev), _mesh(*cases.icosphere_mesh(8), dev)]
-    g = wr.RenderGraph(wr_ctx, [(m, cam) for m in meshes], 64, 64, view_lanes=view_lanes, render_attr=False)
+    g = wr.RenderGraph(wr_ctx, [(m, cam) for m in meshes], 64, 64, view_lanes=view_lanes, stagger=stagger,
+                       render_attr=False)
     for _ in range(3):
         outs = g.replay()
     torch.cuda.synchronize()
@@ -63,3 +66,31 @@ def test_view_lanes_equal_eager(wr_ctx, view_lanes):
     torch.cuda.synchronize()
     _same(o, wr.render(wr_ctx, meshes[0], cam, 64, 64, render_attr=False,
                        depth_normalization_strategy=wr.Zero123PlusPlusNormalization()))
+
+
+@pytest.mark.parametrize("tail", [False, True])
+def test_bake_graph_replay_equals_eager(wr_ctx, tail):
+    """BakeGraph: one CameraProjection call captured as a CUDA graph returns what the eager call returns, also
+    after the images were updated in place; with the padding + Poisson tail as well."""
+    from test_gpu_bake_parity import _setup
+    from worldrenderer_b200 import synth
+    dev = wr_ctx.device
+    mesh, cam, images = _setup(dev)
+    img = torch.from_numpy(images).to(dev)
+    proj = wr.CameraProjection("torch-cuda" if tail else None, None, str(dev), "cuda")
+    kw = dict(uv_size=128, poisson_blending=tail, uv_padding=tail, pb_num_iters=40, depth_grad_dilation=5,
+              uv_exp_blend_alpha=3.0, uv_exp_blend_view_weight=torch.tensor([1.0, 0.5, 1.0, 2.0, 1.0, 1.0]),
+              aoi_cos_valid_threshold=0.2, depth_grad_threshold=0.1, iou_rejection_threshold=None, return_dict=True)
+    g = wr.BakeGraph(proj, img, mesh, cam, **kw)
+    for step in range(2):
+        if step == 1:
+            img.copy_(torch.from_numpy(synth.view_images(6, 96, 96, seed=5)).to(dev))
+        got = g.replay()
+        torch.cuda.synchronize()
+        want = proj(img, mesh, cam, **kw)
+        assert torch.equal(got.uv_proj, want.uv_proj) and torch.equal(got.uv_proj_mask, want.uv_proj_mask)
+        assert torch.equal(got.uv_depth_grad, want.uv_depth_grad) and torch.equal(got.uv_aoi_cos, want.uv_aoi_cos)
+    with pytest.raises(ValueError):
+        wr.BakeGraph(proj, img.cpu(), mesh, cam, **kw)
+    with pytest.raises(ValueError):
+        wr.BakeGraph(proj, img, mesh, cam, masks=torch.ones((6, 96, 96), device=dev), **dict(kw, iou_rejection_threshold=0.8))

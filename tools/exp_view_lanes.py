@@ -12,8 +12,8 @@ m.set_stitched_mesh(m.v_pos, m.t_pos_idx); m.v_nrm
 ctx = wr.NVDiffRastContextWrapper('cuda:0', 'cuda')
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 ref = wr.render(ctx, m, cam, 768, 768, render_attr=False)
-for vl in (1, 2, 3, 6):
-    g = wr.RenderGraph(ctx, [(m, cam)], 768, 768, view_lanes=vl, render_attr=False)
+for vl, st in ((1, False), (2, False), (2, True), (3, False), (3, True), (6, False), (6, True)):
+    g = wr.RenderGraph(ctx, [(m, cam)], 768, 768, view_lanes=vl, stagger=st, render_attr=False)
     for _ in range(5): g.replay()
     torch.cuda.synchronize()
     K = 40
@@ -24,5 +24,5 @@ for vl in (1, 2, 3, 6):
     ms = np.mean([a.elapsed_time(b) for a, b in ev])
     o = g.replay()[0]; torch.cuda.synchronize()
     same = all(torch.equal(getattr(o, n), getattr(ref, n)) for n in ("mask", "pos", "depth", "normal"))
-    print(f'view_lanes {vl}: {ms*1e3:.1f} us per step, {6/ms*1e3:.0f} views/s, identical to eager: {same}')
+    print(f'view_lanes {vl} stagger {st}: {ms*1e3:.1f} us per step, {6/ms*1e3:.0f} views/s, identical to eager: {same}')
     del g

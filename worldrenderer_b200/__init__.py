@@ -26,7 +26,7 @@ from .render import (
     Zero123PlusPlusNormalization,
     render,
 )
-from .graph import RenderGraph
+from .graph import BakeGraph, RenderGraph
 from .smart_paint import SmartPainter
 from .tangent import view_normals_to_tangent_space
 from .utils import (
@@ -59,5 +59,5 @@ __all__ = [
     "SmartPainter", "get_clip_space_position", "image_to_tensor", "make_image_grid", "tensor_to_image",
     "transform_points_homo", "ExponentialBlend", "RandomChoiceBlend", "SimpleUVValidityStrategy", "UVBlendOutput",
     "UVPrecomputeOutput", "UVRenderAttrOutput", "UVRenderGeometryOutput", "uv_blend", "uv_precompute",
-    "uv_render_attr", "uv_render_geometry", "PoissonBlendingSolver", "RenderGraph", "view_normals_to_tangent_space",
+    "uv_render_attr", "uv_render_geometry", "PoissonBlendingSolver", "RenderGraph", "BakeGraph", "view_normals_to_tangent_space",
 ]

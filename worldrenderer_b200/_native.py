@@ -48,6 +48,7 @@ class RenderArgs(ctypes.Structure):
         ("out_mask", ctypes.c_void_p), ("out_pos", ctypes.c_void_p), ("out_depth", ctypes.c_void_p),
         ("out_normal", ctypes.c_void_p), ("out_tangent", ctypes.c_void_p), ("out_geo", ctypes.c_void_p), ("out_attr", ctypes.c_void_p), ("out_tri_id", ctypes.c_void_p),
         ("out_rast", ctypes.c_void_p),
+        ("raster_done_event", ctypes.c_void_p),
     ]
 
 

@@ -585,6 +585,10 @@ extern "C" int wr_render(wr_ctx *ctx, const wr_render_args *args, void *stream_)
                            mask_bytes + (use_pack ? wr_vertex_pack_bytes(A.V, A.Vn, want_nrm) : 0), &res, &extra,
                            stream, use_pack ? &pack : nullptr, fill.nseg ? &fill : nullptr);
     if (rc != WR_OK) return rc;
+    if (A.raster_done_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(A.raster_done_event), stream);
+        if (e != cudaSuccess) return wr_set_cuda_error(ctx, e, "cudaEventRecord(raster_done_event)");
+    }
 
     ShadeParams P;
     P.a = A;

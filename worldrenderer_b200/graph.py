@@ -11,7 +11,10 @@ so the graph holds independent chains: the raster set-up of one mesh is bound by
 pass of another by the latency of its gathers and by its stores, and the two overlap when they run side by side.
 
 `view_lanes > 1` does the same inside ONE job: its views are split into that many groups, each rendered by its own
-chain into a slice of the job's output tensors (the vertex pass runs once per group).
+chain into a slice of the job's output tensors (the vertex pass runs once per group).  With `stagger=True` group
+k + 1 starts when the raster passes of group k are done (an event the library records between the raster passes and
+the shading pass), so that the chains run out of phase: the set-up pass of one group next to the shading pass of the
+previous one instead of two set-up passes competing for the integer pipe.
 
 The output tensors are static: every replay overwrites them.  Vertex positions, faces and cameras are read
 from the tensors the job list held at capture time -- update those in place (copy_) to render new data of the
@@ -30,12 +33,14 @@ from .render import NVDiffRastContextWrapper, RenderOutput, render
 
 class RenderGraph:
     def __init__(self, ctx: NVDiffRastContextWrapper, jobs: Sequence[Tuple[TexturedMesh, Camera]], height: int,
-                 width: int, warmup: int = 2, lanes: int = 1, view_lanes: int = 1, **render_kwargs):
+                 width: int, warmup: int = 2, lanes: int = 1, view_lanes: int = 1, stagger: bool = False,
+                 **render_kwargs):
         if not jobs:
             raise ValueError("RenderGraph needs at least one (mesh, camera) job")
         self.jobs, self.height, self.width = list(jobs), int(height), int(width)
         self.kwargs = dict(render_kwargs)
         self.view_lanes = max(1, int(view_lanes))
+        self.stagger = bool(stagger) and self.view_lanes > 1
         self.lanes = max(1, min(int(lanes), len(self.jobs))) if self.view_lanes == 1 else self.view_lanes
         # contexts of its own: the captured kernels hold pointers into a context's scratch, which an eager call
         # of a larger shape on a shared context would reallocate; one per lane, because concurrent chains cannot
@@ -61,6 +66,13 @@ class RenderGraph:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._lane_streams = [torch.cuda.Stream(dev) for _ in range(self.lanes - 1)]
+        self._raster_events = []
+        if self.stagger:
+            for _ in range(self.view_lanes):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))   # torch creates the CUDA event on the first record
+                self._raster_events.append(ev)
+            torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs: List[RenderOutput] = self._run_lanes()
@@ -74,7 +86,7 @@ class RenderGraph:
         k = min(self.view_lanes, max(n, 1))
         return [slice(n * g // k, n * (g + 1) // k) for g in range(k)]
 
-    def _render_group(self, group: int, job: int) -> None:
+    def _render_group(self, group: int, job: int, raster_done_event=None) -> None:
         """Views `group` of job `job` into the matching slices of the job's static outputs."""
         groups = self._groups(job)
         if group >= len(groups) or groups[group].start == groups[group].stop:
@@ -84,7 +96,8 @@ class RenderGraph:
         full = self._static[job]
         bufs = {name: getattr(full, name)[sl] for name in ("mask", "pos", "depth", "normal", "attr", "tangent")
                 if getattr(full, name, None) is not None}
-        out = render(self.ctxs[group], m, c[sl], self.height, self.width, _out_buffers=bufs, **self.kwargs)
+        out = render(self.ctxs[group], m, c[sl], self.height, self.width, _out_buffers=bufs,
+                     _raster_done_event=raster_done_event, **self.kwargs)
         for name, buf in bufs.items():   # a normaliser / background that allocates its own result: copy it in
             got = getattr(out, name)
             if got.data_ptr() != buf.data_ptr():
@@ -103,8 +116,11 @@ class RenderGraph:
             for g in range(self.view_lanes):
                 stream = main if g == 0 else self._lane_streams[g - 1]
                 with torch.cuda.stream(stream):
+                    if self.stagger and g > 0:
+                        stream.wait_event(self._raster_events[g - 1])   # raster passes of the previous group are done
+                    last = len(self.jobs) - 1
                     for j in range(len(self.jobs)):
-                        self._render_group(g, j)
+                        self._render_group(g, j, self._raster_events[g] if self.stagger and j == last else None)
             for s in self._lane_streams:
                 main.wait_stream(s)
             return list(self._static)
@@ -124,3 +140,59 @@ class RenderGraph:
     def replay(self) -> List[RenderOutput]:
         self.graph.replay()
         return self.outputs
+
+
+class BakeGraph:
+    """CUDA-graph replay of ONE `CameraProjection` call (projection.py:66-204 of the reference) on fixed shapes.
+
+    A bake is a dozen short kernels (view raster + shading, view prep, unprojection, optional padding / Poisson tail)
+    issued from Python; on config C a quarter of the 0.32 ms is launch gaps.  The capture holds the call as it is --
+    same kernels, same arithmetic -- so `replay()` returns what the eager call returns.
+
+    Static inputs: `images` (and `masks`) must be float tensors on the device; update them in place (`copy_`) between
+    replays.  The mesh texture (the "old" atlas the result is stitched with) is read at replay time from
+    `mesh.texture`'s storage.  Not capturable, refused here: IoU rejection with masks (it reads a value back to
+    the host, projection.py:125-138), background removal, cameras built inside the call."""
+
+    def __init__(self, proj, images: torch.Tensor, mesh: TexturedMesh, cam: Camera, warmup: int = 2, masks=None,
+                 **kwargs):
+        from .projection import CameraProjection
+        if not isinstance(images, torch.Tensor) or not images.is_cuda or images.dtype != torch.float32:
+            raise ValueError("BakeGraph: images must be a float32 tensor on the device")
+        if masks is not None and kwargs.get("iou_rejection_threshold", 0.8) is not None:
+            raise ValueError("BakeGraph: pass iou_rejection_threshold=None with masks (the rejection test reads the IoU "
+                             "back to the host)")
+        if masks is not None and (not isinstance(masks, torch.Tensor) or not masks.is_cuda):
+            raise ValueError("BakeGraph: masks must be a tensor on the device")
+        if kwargs.get("remove_bg") or kwargs.get("warp_images") or cam is None:
+            raise ValueError("BakeGraph: remove_bg, warp_images and cam=None are not capturable")
+        dev = images.device
+        # a projection object (raster context, scratch, uv_precompute cache) of its own: the captured kernels hold
+        # pointers into them
+        self.proj = CameraProjection(proj.pb_backend, None, str(dev), proj.ctx.context_type)
+        self.images, self.masks, self.mesh, self.cam = images, masks, mesh, cam
+        vw = kwargs.get("uv_exp_blend_view_weight")
+        if vw is not None:   # a host tensor would be uploaded inside the capture
+            kwargs["uv_exp_blend_view_weight"] = torch.as_tensor(vw).to(device=dev, dtype=torch.float32).contiguous()
+        self.kwargs = kwargs
+        mesh.v_nrm  # lazily computed once, outside the capture
+        import contextlib
+        import io
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(max(1, warmup)):   # scratch growth, uv_precompute and index caches happen here
+                self._call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), contextlib.redirect_stdout(io.StringIO()):
+            self.output = self._call()
+
+    def _call(self):
+        return self.proj(self.images, self.mesh, self.cam, masks=self.masks, **self.kwargs)
+
+    def replay(self):
+        """Runs the captured bake; returns the (static) result of the call -- overwritten by the next replay."""
+        self.graph.replay()
+        return self.output

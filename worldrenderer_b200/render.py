@@ -270,10 +270,12 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
                         want_pos=True, want_depth=True, want_normal=True, want_attr=False, want_tri_id=False,
                         want_rast=False, want_tangent=False, tangent_background=0.0, want_geo=False,
                         depth_normalization_strategy=None, normal_background=0.0,
-                        attr_background=0.5, texture_override=None, texture_filter_mode="linear", out_buffers=None):
+                        attr_background=0.5, texture_override=None, texture_filter_mode="linear", out_buffers=None,
+                        raster_done_event=None):
     """One wr_render call.  Returns a dict of tensors; `mask` is uint8 0/1 (callers view it as bool).
     out_buffers: optional {name: preallocated contiguous tensor} written instead of fresh allocations (RenderGraph
-    renders groups of views into slices of one output)."""
+    renders groups of views into slices of one output).  raster_done_event: a recorded-at-least-once torch.cuda.Event,
+    re-recorded by the library between the raster passes and the shading pass (wr_render_args.raster_done_event)."""
     dev = ctx.device
 
     def _new(name, shape, dtype):
@@ -387,6 +389,11 @@ def render_geometry_raw(ctx: NVDiffRastContextWrapper, mesh: TexturedMesh, cam: 
     if want_rast:
         out["rast"] = _new("rast", (B, H, W, 4), torch.float32)
         a.out_rast = _native.ptr(out["rast"])
+    if raster_done_event is not None:
+        handle = int(raster_done_event.cuda_event)
+        if not handle:
+            raise ValueError("raster_done_event must have been recorded once (torch creates the CUDA event lazily)")
+        a.raster_done_event = handle
     c = ctx.ctx
     c.check(_native.lib().wr_render(c.handle, ctypes.byref(a), c.stream()), "wr_render")
     del keep
@@ -422,6 +429,7 @@ def render(
     texture_override=None,
     texture_filter_mode: str = "linear",
     _out_buffers=None,
+    _raster_done_event=None,
 ) -> RenderOutput:
     """Same signature and outputs as the reference render() (render.py:220-286)."""
     if antialias_attr:
@@ -431,7 +439,8 @@ def render(
         want_attr=render_attr, want_tangent=render_tangent, tangent_background=tangent_background,
         depth_normalization_strategy=depth_normalization_strategy,
         normal_background=normal_background, attr_background=attr_background, texture_override=texture_override,
-        texture_filter_mode=texture_filter_mode, out_buffers=_out_buffers)
+        texture_filter_mode=texture_filter_mode, out_buffers=_out_buffers,
+        raster_done_event=_raster_done_event)
     out = RenderOutput(mask=raw["mask"], pos=raw["pos"], depth=raw.get("depth"), attr=raw.get("attr"),
                        normal=raw.get("normal"))
     out.tangent = raw.get("tangent")
