@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
         s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pack.nrm4 && v < pack.Vn) {
+    if (pack.nrm4 && v < pack.Vn && blockIdx.y == 0) {
         const float *n = pack.v_nrm + 3 * (size_t)v;
         pack.nrm4[v] = make_float4(__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f);
     }
@@ -354,11 +354,13 @@ __device__ __forceinline__ void snap_rec(const float4 c, int W, int H, int addx,
     }
 }
 
+// grid.y > 1: block row y handles the views [y * bper, (y + 1) * bper) (WR_SNAP_SPLIT: more, shorter threads fill the
+// last wave of this short kernel better; the positions are then read once per row, from L2).
 __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H, int addx, int addy, uint2 *rec,
-                                                 int *stats, int nstats, VertexPack pack)
+                                                 int *stats, int nstats, VertexPack pack, int bper)
 {
     wr_pdl_trigger();
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0 && blockIdx.y == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
     constexpr int kStageViews = 32;
     __shared__ float4 s_mvp[kStageViews * 4];
@@ -373,9 +375,10 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H
     if (v >= src.V) return;
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    if (pack.pos4 && blockIdx.y == 0) pack.pos4[v] = make_float4(x, y, z, 0.0f);
     const bool finite_pos = isfinite(x) && isfinite(y) && isfinite(z);
-    for (int b = 0; b < B; ++b) {
+    const int b_lo = blockIdx.y * bper, b_hi = min(B, b_lo + bper);
+    for (int b = b_lo; b < b_hi; ++b) {
         float4 r0, r1, r2, r3;
         if (b < kStageViews) {
             r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
@@ -1418,8 +1421,12 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
             M.depth = depth; M.queue = queue; M.Fq = F; M.counters = stats;
             P.sv = nullptr;  // the queue pass recomputes the few snapped vertices it needs
             // stored = snapped (centred) + 8 W - 8 (relative to the sample of pixel 0) + 16 lo_c (bias)
-            k_snap_mv<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
-                src, B, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec, stats, B * 8, vp);
+#ifndef WR_SNAP_SPLIT
+#define WR_SNAP_SPLIT 1
+#endif
+            const int snap_rows = B < WR_SNAP_SPLIT ? B : WR_SNAP_SPLIT, bper = (B + snap_rows - 1) / snap_rows;
+            k_snap_mv<<<dim3(wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), wr_div_up(B, bper)), 256, 0, stream>>>(
+                src, B, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec, stats, B * 8, vp, bper);
             WR_CHECK_LAUNCH(ctx, "k_snap_mv");
             wr_stage(ctx, stream, "k_setup_triangles");
             const bool pdl = !ctx->profiling;
