@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) k_snap_vertices_allviews(VtxSrc src, int 
         s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pack.nrm4 && v < pack.Vn && blockIdx.y == 0) {
+    if (pack.nrm4 && v < pack.Vn) {
         const float *n = pack.v_nrm + 3 * (size_t)v;
         pack.nrm4[v] = make_float4(__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f);
     }
@@ -354,13 +354,11 @@ __device__ __forceinline__ void snap_rec(const float4 c, int W, int H, int addx,
     }
 }
 
-// grid.y > 1: block row y handles the views [y * bper, (y + 1) * bper) (WR_SNAP_SPLIT: more, shorter threads fill the
-// last wave of this short kernel better; the positions are then read once per row, from L2).
 __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H, int addx, int addy, uint2 *rec,
-                                                 int *stats, int nstats, VertexPack pack, int bper)
+                                                 int *stats, int nstats, VertexPack pack)
 {
     wr_pdl_trigger();
-    if (blockIdx.x == 0 && blockIdx.y == 0)
+    if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
     constexpr int kStageViews = 32;
     __shared__ float4 s_mvp[kStageViews * 4];
@@ -375,10 +373,9 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H
     if (v >= src.V) return;
     const float *p = src.pos + 3 * (size_t)v;
     const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    if (pack.pos4 && blockIdx.y == 0) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
     const bool finite_pos = isfinite(x) && isfinite(y) && isfinite(z);
-    const int b_lo = blockIdx.y * bper, b_hi = min(B, b_lo + bper);
-    for (int b = b_lo; b < b_hi; ++b) {
+    for (int b = 0; b < B; ++b) {
         float4 r0, r1, r2, r3;
         if (b < kStageViews) {
             r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
@@ -496,46 +493,6 @@ __device__ __forceinline__ void mv_fast(const MvParams &P, unsigned xy0, unsigne
     const int area2 = E0 + E1 + E2;
     const bool flip = lo < 0;
     const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
-    const float w0 = __int2float_rn(E0) * inv_area;
-    const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
-    const float w2 = (1.0f - w0) - w1;
-    float zw = ((z0 * w0) + ((flip ? z2 : z1) * w1)) + ((flip ? z1 : z2) * w2);
-    zw = zw + 0.0f;
-    if (zw >= -1.0f && zw <= 1.0f) {
-        const unsigned rel = pxy - P.lo_px;  // no borrow: the sample lies in the viewport
-        resolve_sample(depth_view + ((rel >> 16) * (unsigned)P.W + (rel & 0xFFFFu)), zw, id);
-    }
-}
-
-#ifndef WR_MV_SPLIT
-#define WR_MV_SPLIT 0
-#endif
-// mv_fast in two halves, for k_setup_mvc: the coverage test (same perturbed cross products) ...
-__device__ __forceinline__ bool mv_fast_test(unsigned xy0, unsigned xy1, unsigned xy2, unsigned pxy)
-{
-    const int pc = (int)(pxy & 0xFFFFu), pr = (int)(pxy >> 16);
-    const int cx = (pc << 14) + 32, cy = (pr << 14) + 1;
-    const int a0 = (int)(xy0 & 0xFFFFu) * 1024 - cx, b0 = (int)(xy0 >> 16) * 1024 - cy;
-    const int a1 = (int)(xy1 & 0xFFFFu) * 1024 - cx, b1 = (int)(xy1 >> 16) * 1024 - cy;
-    const int a2 = (int)(xy2 & 0xFFFFu) * 1024 - cx, b2 = (int)(xy2 >> 16) * 1024 - cy;
-    const int Q0 = a1 * b2 - a2 * b1, Q1 = a2 * b0 - a0 * b2, Q2 = a0 * b1 - a1 * b0;
-    const int lo = __vimin3_s32(Q0, Q1, Q2), hi = __vimax3_s32(Q0, Q1, Q2);
-    return !(lo <= 0 && hi >= 0);
-}
-
-// ... and depth + resolve of a sample that passed it.  The Q_i of a covered sample share the sign of the doubled
-// area (their sum is 2^20 * area2), so mv_fast's `flip = lo < 0` is `area2 < 0` here: same expressions, same bits.
-__device__ __forceinline__ void mv_fast_hit(const MvParams &P, unsigned xy0, unsigned xy1, unsigned xy2, float z0,
-                                            float z1, float z2, unsigned long long *depth_view, unsigned pxy, uint32_t id)
-{
-    const int px = (int)(pxy & 0xFFFFu) << 4, py = (int)(pxy >> 16) << 4;
-    const int u0 = (int)(xy0 & 0xFFFFu) - px, v0 = (int)(xy0 >> 16) - py;
-    const int u1 = (int)(xy1 & 0xFFFFu) - px, v1 = (int)(xy1 >> 16) - py;
-    const int u2 = (int)(xy2 & 0xFFFFu) - px, v2 = (int)(xy2 >> 16) - py;
-    const int E0 = u1 * v2 - u2 * v1, E1 = u2 * v0 - u0 * v2, E2 = u0 * v1 - u1 * v0;
-    const int area2 = E0 + E1 + E2;
-    const bool flip = area2 < 0;
-    const float inv_area = 1.0f / __int2float_rn(area2);
     const float w0 = __int2float_rn(E0) * inv_area;
     const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
     const float w2 = (1.0f - w0) - w1;
@@ -672,29 +629,7 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
                 const float z0 = __uint_as_float(ra.y), z1 = __uint_as_float(rc.y), z2 = __uint_as_float(rd.y);
                 unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
                 const unsigned mn = __vimin3_u16x2(a, c, d), mx = __vimax3_u16x2(a, c, d);
-#if WR_MV_SPLIT
                 if (((mx - mn) & 0xFFE0FFE0u) == 0u) {
-                    // spans less than two pixels: 1, 2 or 2 x 2 samples (bit j = column j & 1, row j >> 1): coverage of
-                    // all of them first, then depth + resolve of the covered ones, so that a warp runs the long
-                    // stretch once (twice when some lane covers two samples) instead of once per sample turn
-                    const unsigned ex = tt & 1u, ey = (tt >> 16) & 1u;
-                    unsigned pend = 1u | (ex << 1) | (ey << 2) | ((ex & ey) << 3), hits = 0u;
-#pragma unroll 1
-                    while (pend) {
-                        const unsigned j = __ffs(pend) - 1u;
-                        pend &= pend - 1u;
-                        if (mv_fast_test(a, c, d, first + (j & 1u) + ((j & 2u) << 15))) hits |= 1u << j;
-                    }
-#pragma unroll 1
-                    while (hits) {
-                        const unsigned j = __ffs(hits) - 1u;
-                        hits &= hits - 1u;
-                        mv_fast_hit(P, a, c, d, z0, z1, z2, depth_view, first + (j & 1u) + ((j & 2u) << 15), (uint32_t)t);
-                    }
-                } else if (false) {
-#else
-                if (((mx - mn) & 0xFFE0FFE0u) == 0u) {
-#endif
                     // spans less than two pixels: 1, 2 or 2 x 2 samples
                     mv_fast(P, a, c, d, z0, z1, z2, depth_view, first, (uint32_t)t);
                     if (tt != kGuard) {
@@ -727,134 +662,6 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
         }
     }
     mv_push(P, push, b, entry, lane);
-}
-
-#ifndef WR_MV_COMPACT
-#define WR_MV_COMPACT 0
-#endif
-#ifndef WR_MVC_ROUNDS
-#define WR_MVC_ROUNDS 8
-#endif
-
-// One parked sample: gather the triangle's records again (L1 / L2 hits), depth, resolve.
-__device__ __forceinline__ void mvc_drain_one(const MvParams &P, unsigned vb, unsigned long long *depth_view, uint2 e)
-{
-    const uint32_t t = e.x;
-    const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1), i2 = __ldg(P.tri + 3 * (size_t)t + 2);
-    const uint2 ra = __ldg(P.rec + (vb + (unsigned)i0)), rc = __ldg(P.rec + (vb + (unsigned)i1)),
-                rd = __ldg(P.rec + (vb + (unsigned)i2));
-    mv_fast_hit(P, ra.x, rc.x, rd.x, __uint_as_float(ra.y), __uint_as_float(rc.y), __uint_as_float(rd.y), depth_view, e.y, t);
-}
-
-// k_setup_mv with the covered samples compacted per warp.  Of the (view, triangle) pairs of a sub-pixel mesh about
-// half have a sample in their box and under a fifth cover it, so in k_setup_mv the most expensive stretch -- edge
-// functions, division, depth, address, atomic: ~75 instructions -- runs with ~6 of 32 lanes.  Here a thread walks
-// WR_MVC_ROUNDS pairs; every covered sample is parked as (triangle, sample) in a 256-entry ring of the warp's own
-// shared memory (ballot + popcount give the slots: no atomics, no block barrier), and after each round, while 32 or
-// more are waiting, all lanes take one each.  The ring holds < 32 entries when a round starts and a round adds at
-// most 4 per lane, so 256 entries cannot overflow.  Arithmetic and results are k_setup_mv's.
-__global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mvc(const __grid_constant__ MvParams P,
-                                                               const __grid_constant__ RasterParams Pold,
-                                                               const __grid_constant__ VtxSrc src,
-                                                               const __grid_constant__ FillJob fill)
-{
-    __shared__ uint2 s_ring[8 * 256];   // per warp: 256 x (triangle, sample)
-    wr_pdl_wait();
-    wr_pdl_trigger();
-    wr_fill_share(fill, blockIdx.y * gridDim.x + blockIdx.x);
-    const int b = blockIdx.y;
-    const unsigned lane = threadIdx.x & 31;
-    uint2 *q = s_ring + (threadIdx.x >> 5) * 256;
-    unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
-    const unsigned vb = (unsigned)b * (unsigned)P.V;   // B * V < 2^31 (checked by the launcher)
-    unsigned head = 0, cnt = 0;
-#pragma unroll 1
-    for (int r = 0; r < WR_MVC_ROUNDS; ++r) {
-        const int t0 = (blockIdx.x * WR_MVC_ROUNDS + r) * 256;
-        if (t0 >= P.F) break;   // uniform over the block
-        const int t = t0 + (int)threadIdx.x;
-        unsigned a = 0u, c = 0u, d = 0u, first = 0u, pending = 0u;
-        bool rare = false;   // a vertex without a record, or a box wider than two pixels: handled after the hot loop
-        if (t < P.F) {
-            const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1), i2 = __ldg(P.tri + 3 * (size_t)t + 2);
-            if (__vimax3_u32((unsigned)i0, (unsigned)i1, (unsigned)i2) < (unsigned)P.V) {
-                a = __ldg(&P.rec[vb + (unsigned)i0].x); c = __ldg(&P.rec[vb + (unsigned)i1].x); d = __ldg(&P.rec[vb + (unsigned)i2].x);
-                const unsigned tt = mv_box(a, c, d, P.lo_px, P.hi_px, first);
-                if (__vimin3_u32(a, c, d) == 0u) {   // a record's halves are >= 2760
-                    rare = true;
-                } else if ((tt & kGuard) == kGuard) {
-                    const unsigned span = __vimax3_u16x2(a, c, d) - __vimin3_u16x2(a, c, d);
-                    if ((span & 0xFFE0FFE0u) == 0u) {
-                        // spans less than two pixels: 1, 2 or 2 x 2 samples; bit j = sample (column j & 1, row j >> 1)
-                        const unsigned ex = tt & 1u, ey = (tt >> 16) & 1u;
-                        pending = 1u | (ex << 1) | (ey << 2) | ((ex & ey) << 3);
-                    } else {
-                        rare = true;
-                    }
-                }
-            }
-        }
-        // coverage of the box's samples (divergent: lanes with more samples loop longer), hits as a 4-bit mask
-        unsigned hits = 0u;
-#pragma unroll 1
-        while (pending) {
-            const unsigned j = __ffs(pending) - 1u;
-            pending &= pending - 1u;
-            if (mv_fast_test(a, c, d, first + (j & 1u) + ((j & 2u) << 15))) hits |= 1u << j;
-        }
-        // every lane from here on: park the hits, one per lane and turn (a second turn is rare)
-#pragma unroll 1
-        while (__any_sync(0xFFFFFFFFu, hits != 0u)) {
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, hits != 0u);
-            if (hits) {
-                const unsigned j = __ffs(hits) - 1u;
-                hits &= hits - 1u;
-                q[(head + cnt + __popc(m & ((1u << lane) - 1u))) & 255u] =
-                    make_uint2((uint32_t)t, first + (j & 1u) + ((j & 2u) << 15));
-            }
-            cnt += __popc(m);
-        }
-        int push = 0;
-        uint32_t entry = (uint32_t)t;
-        if (__any_sync(0xFFFFFFFFu, rare)) {
-            if (rare) {   // k_setup_mv's other branches, from the records gathered again
-                const int i0 = __ldg(P.tri + 3 * (size_t)t), i1 = __ldg(P.tri + 3 * (size_t)t + 1), i2 = __ldg(P.tri + 3 * (size_t)t + 2);
-                const uint2 ra = __ldg(P.rec + (vb + (unsigned)i0)), rc = __ldg(P.rec + (vb + (unsigned)i1)),
-                            rd = __ldg(P.rec + (vb + (unsigned)i2));
-                if (__vimin3_u32(ra.x, rc.x, rd.x) == 0u) {
-                    mv_cold(Pold, src, b, i0, i1, i2, t, depth_view, push, entry);
-                } else {
-                    unsigned f2;
-                    const unsigned tt = mv_box(ra.x, rc.x, rd.x, P.lo_px, P.hi_px, f2);
-                    const unsigned span = __vimax3_u16x2(ra.x, rc.x, rd.x) - __vimin3_u16x2(ra.x, rc.x, rd.x);
-                    const float z0 = __uint_as_float(ra.y), z1 = __uint_as_float(rc.y), z2 = __uint_as_float(rd.y);
-                    const unsigned rel = f2 - P.lo_px;  // no borrow: first >= lo_px in both halves
-                    const int c0 = (int)(rel & 0xFFFFu), r0 = (int)(rel >> 16);
-                    const int nx = (int)(tt & 0xFFFu), ny = (int)((tt >> 16) & 0xFFFu);  // box = (nx + 1) x (ny + 1) samples
-                    if ((nx + 1) * (ny + 1) <= 4 && (span & 0xFF80FF80u) == 0u) {
-                        // a sliver of up to four samples that spans less than eight pixels (exact in int32)
-#pragma unroll 1
-                        for (int rr = r0; rr <= r0 + ny; ++rr)
-#pragma unroll 1
-                            for (int cc = c0; cc <= c0 + nx; ++cc)
-                                mv_single(P, ra.x, rc.x, rd.x, z0, z1, z2, b, cc, rr, (uint32_t)t);
-                    } else {
-                        mv_multi(P, ra.x, rc.x, rd.x, z0, z1, z2, b, (uint32_t)t, push);
-                    }
-                }
-            }
-            mv_push(P, push, b, entry, lane);
-        }
-        __syncwarp();
-#pragma unroll 1
-        while (cnt >= 32u) {
-            mvc_drain_one(P, vb, depth_view, q[(head + lane) & 255u]);
-            head = (head + 32u) & 255u;
-            cnt -= 32u;
-        }
-        __syncwarp();
-    }
-    if (lane < cnt) mvc_drain_one(P, vb, depth_view, q[(head + lane) & 255u]);
 }
 
 // One warp rasterises one snapped triangle (or the stripe-th share of its 16x16 blocks).
@@ -1421,20 +1228,13 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
             M.depth = depth; M.queue = queue; M.Fq = F; M.counters = stats;
             P.sv = nullptr;  // the queue pass recomputes the few snapped vertices it needs
             // stored = snapped (centred) + 8 W - 8 (relative to the sample of pixel 0) + 16 lo_c (bias)
-#ifndef WR_SNAP_SPLIT
-#define WR_SNAP_SPLIT 1
-#endif
-            const int snap_rows = B < WR_SNAP_SPLIT ? B : WR_SNAP_SPLIT, bper = (B + snap_rows - 1) / snap_rows;
-            k_snap_mv<<<dim3(wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), wr_div_up(B, bper)), 256, 0, stream>>>(
-                src, B, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec, stats, B * 8, vp, bper);
+            k_snap_mv<<<wr_div_up(vp.nrm4 && vp.Vn > V ? vp.Vn : V, 256), 256, 0, stream>>>(
+                src, B, W, H, 8 * W - 8 + 16 * lo_c, 8 * H - 8 + 16 * lo_r, rec, stats, B * 8, vp);
             WR_CHECK_LAUNCH(ctx, "k_snap_mv");
             wr_stage(ctx, stream, "k_setup_triangles");
             const bool pdl = !ctx->profiling;
-            wr_fill_plan(&FJ, (unsigned)(wr_div_up(F, WR_MV_COMPACT ? 256 * WR_MVC_ROUNDS : 256) * B));
-            if (WR_MV_COMPACT)
-                wr_launch(k_setup_mvc, dim3(wr_div_up(F, 256 * WR_MVC_ROUNDS), B), dim3(256), stream, pdl, M, P, src, FJ);
-            else
-                wr_launch(k_setup_mv, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, M, P, src, FJ);
+            wr_fill_plan(&FJ, (unsigned)(wr_div_up(F, 256) * B));
+            wr_launch(k_setup_mv, dim3(wr_div_up(F, 256), B), dim3(256), stream, pdl, M, P, src, FJ);
             WR_CHECK_LAUNCH(ctx, "k_setup_mv");
             wr_stage(ctx, stream, "k_raster_queues");
             wr_launch(k_raster_queues, dim3(qgrid, B), dim3(256), stream, pdl, P, src, 0);
