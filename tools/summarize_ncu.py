@@ -21,3 +21,8 @@ for r in rows[2:]:
     for k in KEYS:
         if k in d:
             print(f"   {k:75s} {d[k]:>16s} {units[hdr.index(k)]}")
+    if "--stalls" in sys.argv:   # warp-state shares: where the resident warps spend their cycles
+        st = [(k, float(d[k].replace(",", ""))) for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and
+              k.endswith("_per_issue_active.ratio") and d.get(k) not in (None, "", "n/a")]
+        for k, x in sorted(st, key=lambda kv: -kv[1])[:8]:
+            print(f"   stall {k[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:40s} {x:8.2f} warps per issue")

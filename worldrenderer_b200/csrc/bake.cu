@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
                 const float s20 = c[dw - 1], s21 = c[dw], s22 = c[dw + 1];
                 const float gx = ((((s00 - s02) + 2.0f * s10) - 2.0f * s12) + s20) - s22;
                 const float gy = ((((s00 + 2.0f * s01) + s02) - s20) - 2.0f * s21) - s22;
-                g = sqrtf(gx * gx + gy * gy);
+                g = wr_sqrt_z(gx * gx + gy * gy);   // flat depth: gradient exactly 0
             }
             s_g[gy_ * gw + gx_] = g;
         };
@@ -270,7 +270,19 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
     float *s_expo = s_cam + A.Nv * 16;
     for (int i = threadIdx.x; i < A.Nv; i += blockDim.x)
         s_expo[i] = A.view_weight ? A.alpha / A.view_weight[i] : A.alpha;
+    // bit v: row 3 of view v's matrix is exactly (0 0 0 1) -- an orthographic view (views beyond 32: general path)
+    __shared__ unsigned s_unit_rows;
+    if (threadIdx.x < 32) {
+        bool unit = false;
+        if ((int)threadIdx.x < A.Nv) {
+            const float *m = A.mvp + 16 * threadIdx.x + 12;
+            unit = m[0] == 0.0f && m[1] == 0.0f && m[2] == 0.0f && m[3] == 1.0f;
+        }
+        const unsigned bits = __ballot_sync(0xFFFFFFFFu, unit);
+        if (threadIdx.x == 0) s_unit_rows = bits;
+    }
     __syncthreads();
+    unsigned unit_rows = s_unit_rows;
 
     const long long ntex = (long long)A.Hu * A.Wu;
     const long long o = A.tex_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,19 +296,25 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
         const float ux = up[0], uy = up[1], uz = up[2];
         const long long npix = (long long)A.H * A.W;
         bool valid0 = false;
+        // a finite texel under a (0 0 0 1) row has w = ((0 x + 0 y) + 0 z) + 1 = 1 exactly (a non-finite one: NaN)
+        if (!(isfinite(ux) && isfinite(uy) && isfinite(uz))) unit_rows = 0u;
         for (int v = 0; v < A.Nv; ++v) {
             const float *m = s_cam + 16 * v;
             const float cx = ((m[0] * ux + m[1] * uy) + m[2] * uz) + m[3];
             const float cy = ((m[4] * ux + m[5] * uy) + m[6] * uz) + m[7];
-            const float cw = ((m[12] * ux + m[13] * uy) + m[14] * uz) + m[15];
-            // uv.py:90, no w > 0 guard.  x / 1 == x exactly: an orthographic view (w is exactly 1 for every texel)
-            // skips the two IEEE divisions, ~40 instructions of the ~210 per texel and view
-            const bool unit_w = cw == 1.0f;
-            const float gx = unit_w ? cx : cx / cw, gy = unit_w ? cy : cy / cw;
+            // uv.py:90, no w > 0 guard.  x / 1 == x exactly: an orthographic view skips the w row and the two IEEE
+            // divisions behind a branch that is uniform in practice (a select would still execute them, and a texel
+            // outside the charts -- clip x exactly 0 -- sends the whole warp through the division's slow path)
+            float gx = cx, gy = cy;
+            if (!(v < 32 && ((unit_rows >> v) & 1u))) {
+                const float cw = ((m[12] * ux + m[13] * uy) + m[14] * uz) + m[15];
+                gx = cx / cw;
+                gy = cy / cw;
+            }
             const Bilinear t = make_bilinear(gx, gy, A.W, A.H);
             const float4 geo = sample4(reinterpret_cast<const float4 *>(A.geo_map) + v * npix, t, A.W, A.H);
             const float dx = geo.x - ux, dy = geo.y - uy, dz = geo.z - uz;
-            const float err = sqrtf((dx * dx + dy * dy) + dz * dz);
+            const float err = wr_sqrt_z((dx * dx + dy * dy) + dz * dz);
             bool valid = (err < A.pos_error_eps) && (geo.w > A.aoi_cos_thresh) && inside;
             // the colour / depth-gradient taps only matter for a texel that passed the geometry test
             float4 att = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -356,9 +374,10 @@ __global__ void __launch_bounds__(256) k_uv_unproject(wr_unproject_args A)
         if (A.out_attr) {
             float o0 = 0.f, o1 = 0.f, o2 = 0.f;
             if (A.old_attr) { o0 = A.old_attr[3 * o]; o1 = A.old_attr[3 * o + 1]; o2 = A.old_attr[3 * o + 2]; }
-            A.out_attr[3 * o] = (sr / den) * va + o0 * (1.0f - va);
-            A.out_attr[3 * o + 1] = (sg / den) * va + o1 * (1.0f - va);
-            A.out_attr[3 * o + 2] = (sb / den) * va + o2 * (1.0f - va);
+            // den >= 1e-5 > 0; a texel without a valid view has sums of exactly 0
+            A.out_attr[3 * o] = wr_div_zpos(sr, den) * va + o0 * (1.0f - va);
+            A.out_attr[3 * o + 1] = wr_div_zpos(sg, den) * va + o1 * (1.0f - va);
+            A.out_attr[3 * o + 2] = wr_div_zpos(sb, den) * va + o2 * (1.0f - va);
         }
     }
 }
@@ -376,9 +395,9 @@ __global__ void __launch_bounds__(256) k_uv_finalize(const float *accum, const f
     if (out_attr) {
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
         if (old_attr) { o0 = old_attr[3 * o]; o1 = old_attr[3 * o + 1]; o2 = old_attr[3 * o + 2]; }
-        out_attr[3 * o] = (a[0] / den) * va + o0 * (1.0f - va);
-        out_attr[3 * o + 1] = (a[1] / den) * va + o1 * (1.0f - va);
-        out_attr[3 * o + 2] = (a[2] / den) * va + o2 * (1.0f - va);
+        out_attr[3 * o] = wr_div_zpos(a[0], den) * va + o0 * (1.0f - va);
+        out_attr[3 * o + 1] = wr_div_zpos(a[1], den) * va + o1 * (1.0f - va);
+        out_attr[3 * o + 2] = wr_div_zpos(a[2], den) * va + o2 * (1.0f - va);
     }
 }
 
@@ -470,9 +489,9 @@ __global__ void __launch_bounds__(256) k_uv_reduce_finalize_p2p(wr_p2p_reduce_ar
                     const float *op = A.old_attr + 3 * (t0 + 4 * q + k);
                     o0 = op[0]; o1 = op[1]; o2 = op[2];
                 }
-                res[3 * k] = (a[0] / den) * va + o0 * (1.0f - va);
-                res[3 * k + 1] = (a[1] / den) * va + o1 * (1.0f - va);
-                res[3 * k + 2] = (a[2] / den) * va + o2 * (1.0f - va);
+                res[3 * k] = wr_div_zpos(a[0], den) * va + o0 * (1.0f - va);
+                res[3 * k + 1] = wr_div_zpos(a[1], den) * va + o1 * (1.0f - va);
+                res[3 * k + 2] = wr_div_zpos(a[2], den) * va + o2 * (1.0f - va);
                 ap[k] = any ? 1 : 0;
             }
             const long long t = t0 + 4 * q;
@@ -557,9 +576,9 @@ __global__ void __launch_bounds__(T) k_uv_reduce_finalize_mc(wr_p2p_reduce_args 
                     const float *op = A.old_attr + 3 * (t0 + 4 * q + k);
                     o0 = op[0]; o1 = op[1]; o2 = op[2];
                 }
-                res[3 * k] = (a[0] / den) * va + o0 * (1.0f - va);
-                res[3 * k + 1] = (a[1] / den) * va + o1 * (1.0f - va);
-                res[3 * k + 2] = (a[2] / den) * va + o2 * (1.0f - va);
+                res[3 * k] = wr_div_zpos(a[0], den) * va + o0 * (1.0f - va);
+                res[3 * k + 1] = wr_div_zpos(a[1], den) * va + o1 * (1.0f - va);
+                res[3 * k + 2] = wr_div_zpos(a[2], den) * va + o2 * (1.0f - va);
                 anyw |= (any ? 1u : 0u) << (8 * k);
             }
             const long long t = t0 + 4 * q;

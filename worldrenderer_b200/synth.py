@@ -126,7 +126,8 @@ def view_images(num_views: int, height: int, width: int, seed: int = 1) -> np.nd
     phi = rng.uniform(0.0, 2.0 * np.pi, (num_views, 3))
     y, x = np.meshgrid(np.arange(height, dtype=np.float64), np.arange(width, dtype=np.float64), indexing="ij")
     arg = omega[None, :, 0, None, None] * x + omega[None, :, 1, None, None] * y + phi[:, :, None, None]
-    return (0.5 + 0.5 * np.sin(arg)).transpose(0, 2, 3, 1).astype(np.float32)
+    # channels-last IN MEMORY, like a decoded image (a transposed view would make every consumer copy it)
+    return np.ascontiguousarray((0.5 + 0.5 * np.sin(arg)).transpose(0, 2, 3, 1), dtype=np.float32)
 
 
 def save_npz(path: str, vertices: np.ndarray, faces: np.ndarray) -> str:

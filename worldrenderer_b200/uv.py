@@ -391,6 +391,25 @@ def fused_view_maps(ctx, mesh, cam, images, H, W, dilation):
     return raw["mask"], raw["geo"], att
 
 
+_VW_CACHE: list = []   # [(source tensor kept alive, version, device, device copy)], last four
+
+
+def _view_weight_on(dev, view_weight) -> torch.Tensor:
+    """The per-view blend weights as a flat float32 tensor on `dev`.  Callers pass a small HOST tensor with every bake
+    (projection.py:87); uploading it is a synchronous pageable copy per call, so the copy of an unchanged tensor is
+    reused (same object, same version counter)."""
+    t = torch.as_tensor(view_weight)
+    if t.device == dev:
+        return _f32c(t).reshape(-1)
+    for src, ver, d, out in _VW_CACHE:
+        if src is t and ver == t._version and d == dev:
+            return out
+    out = _f32c(t.to(dev)).reshape(-1)
+    _VW_CACHE.append((t, t._version, dev, out))
+    del _VW_CACHE[:-4]
+    return out
+
+
 def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, geo, att, view_masks=None, *,
                     pos_error_eps=1e-3, aoi_cos_thresh=0.1, mask_thresh=0.9, depth_grad_thresh=None,
                     first_view_dominate=False, alpha=1.0, view_weight=None, want_per_view=False,
@@ -413,7 +432,7 @@ def fused_unproject(ctx, pre: UVPrecomputeOutput, cam: Camera, H: int, W: int, g
     a.first_view_dominate = int(bool(first_view_dominate))
     a.alpha = float(alpha)
     if view_weight is not None:
-        vw = _f32c(torch.as_tensor(view_weight).to(dev)).reshape(-1)
+        vw = _view_weight_on(dev, view_weight)
         if vw.shape[0] != Nv:
             raise ValueError("view_weight must have one entry per view")
         keep.append(vw)
