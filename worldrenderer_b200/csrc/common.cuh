@@ -153,9 +153,16 @@ static inline void wr_fill_plan(FillJob *J, unsigned nblocks)
     for (int s = 0; s < J->nseg; ++s) J->seg[s].chunk = (J->seg[s].n16 + J->shares - 1) / J->shares;
 }
 
+// Build switch of the background prefill: measured slower than letting the shading pass write the background
+// (DESIGN.md 5b), so it is off and the set-up kernels do not even test for a job (3 % of k_setup_mv's instructions).
+#ifndef WR_PREFILL
+#define WR_PREFILL 0
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void wr_fill_share(const FillJob &J, unsigned bid)
 {
+    if (!WR_PREFILL) return;
     if (J.nseg == 0) return;
     if (bid % J.stride != 0) return;
     const unsigned share = bid / J.stride;

@@ -569,22 +569,22 @@ __device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsign
     }
 }
 
-// queue append of the lanes with push != 0, aggregated per (view, queue) with one atomic each
-__device__ __forceinline__ void mv_push(const MvParams &P, int push, int b, uint32_t entry, unsigned lane)
+// Queue append of a lane with push != 0.  Pushes are rare on this path (a fine mesh queues a triangle only when its
+// box holds more than 64 samples), so the common case must cost nothing: no warp-wide vote -- the lanes that do get
+// here aggregate among themselves (whoever is active shares one atomic per queue).
+__device__ __forceinline__ void mv_push(const MvParams &P, int push, int b, uint32_t entry)
 {
-    if (__ballot_sync(0xFFFFFFFFu, push != 0) == 0) return;
-    const unsigned key = push ? (unsigned)((b << 1) | (push - 1)) : (0x40000000u | lane);
-    const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+    if (push == 0) return;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned m = __match_any_sync(__activemask(), (unsigned)push);   // same view for the whole block
     const int leader = __ffs(m) - 1;
     int base = 0;
-    if (push && (int)lane == leader) base = atomicAdd(P.counters + 4 * b + (push - 1), __popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (push) {
-        const int slot = base + __popc(m & ((1u << lane) - 1u));
-        uint32_t *qv = P.queue + (size_t)b * P.Fq;
-        if (push == 1) qv[slot] = entry;
-        else qv[P.Fq - 1 - slot] = entry;
-    }
+    if ((int)lane == leader) base = atomicAdd(P.counters + 4 * b + (push - 1), __popc(m));
+    base = __shfl_sync(m, base, leader);
+    const int slot = base + __popc(m & ((1u << lane) - 1u));
+    uint32_t *qv = P.queue + (size_t)b * P.Fq;
+    if (push == 1) qv[slot] = entry;
+    else qv[P.Fq - 1 - slot] = entry;
 }
 
 // cold (view, triangle) pair: the contract's own classification from the full snapped vertices
@@ -609,7 +609,6 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
     wr_fill_share(fill, blockIdx.y * gridDim.x + blockIdx.x);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    const unsigned lane = threadIdx.x & 31;
     int push = 0;
     uint32_t entry = (uint32_t)t;
     if (t < P.F) {
@@ -661,7 +660,7 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
             }
         }
     }
-    mv_push(P, push, b, entry, lane);
+    mv_push(P, push, b, entry);
 }
 
 // One warp rasterises one snapped triangle (or the stripe-th share of its 16x16 blocks).
