@@ -101,7 +101,9 @@ class Camera:
         elif not isinstance(index, (slice, list)):
             raise NotImplementedError
         picked = {name: getattr(self, name) for name in _FIELDS}
-        return Camera(**{name: None if t is None else t[index] for name, t in picked.items()})
+        # (the matrices of a strided sub-batch are made contiguous once, here, not by every call that reads them)
+        return Camera(**{name: None if t is None else (t[index] if name == "cam_pos" else t[index].contiguous())
+                         for name, t in picked.items()})
 
     def to(self, device: Optional[str] = None):
         for name in _FIELDS:
@@ -115,7 +117,9 @@ class Camera:
 
 def _assemble(c2w: Optional[torch.Tensor], w2c: Optional[torch.Tensor], proj: torch.Tensor) -> Camera:
     if w2c is None:
-        w2c = torch.linalg.inv(c2w)
+        # torch.linalg.inv hands back column-major matrices (strides (16, 1, 4)): the same values made row-major once
+        # here, instead of a copy kernel in front of every render() / bake that reads them
+        w2c = torch.linalg.inv(c2w).contiguous()
     return Camera(c2w=c2w, w2c=w2c, proj_mtx=proj, mvp_mtx=proj @ w2c, cam_pos=None if c2w is None else c2w[:, :3, 3])
 
 
