@@ -34,8 +34,13 @@ def timed(fn, reps=8):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 res = {}
-for ch in (1, 2, 4, 8, 16):
-    res[f"chunks_{ch}"] = round(timed(lambda: parallel.sharded_bake(ctx, mesh, c, img, UV, chunks=ch, **kw)), 3)
+for shape in ("falling", "equal"):
+    for ch in (1, 2, 3, 4, 6, 8, 12):
+        if ch == 1 and shape == "equal":
+            continue
+        res[f"{shape}_{ch}"] = round(timed(lambda: parallel.sharded_bake(ctx, mesh, c, img, UV, chunks=ch, chunk_shape=shape, **kw)), 3)
+for ch in (4,):   # repeat: run-to-run spread on this box
+    res[f"falling_{ch}_again"] = round(timed(lambda: parallel.sharded_bake(ctx, mesh, c, img, UV, chunks=ch, **kw)), 3)
 if rank == 0:
     print(res)
 dist.destroy_process_group()
