@@ -360,51 +360,71 @@ __global__ void __launch_bounds__(256) k_snap_mv(VtxSrc src, int B, int W, int H
     wr_pdl_trigger();
     if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < nstats; i += blockDim.x) stats[i] = 0;
+    // The views go through shared memory in groups of 32: the inner loop reads its matrix rows from there and its
+    // orthographic flag from one bit mask (a per-iteration choice between a staged and a global row was compiled
+    // into both loads and a select, a fifth of this issue-bound kernel's instructions).
     constexpr int kStageViews = 32;
     __shared__ float4 s_mvp[kStageViews * 4];
-    for (int i = threadIdx.x; i < min(B, kStageViews) * 4; i += blockDim.x)
-        s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + i);
-    __syncthreads();
+    __shared__ unsigned s_unit;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (pack.nrm4 && v < pack.Vn) {
         const float *n = pack.v_nrm + 3 * (size_t)v;
         pack.nrm4[v] = make_float4(__ldg(n), __ldg(n + 1), __ldg(n + 2), 0.0f);
     }
-    if (v >= src.V) return;
-    const float *p = src.pos + 3 * (size_t)v;
-    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    const bool live = v < src.V;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+        const float *p = src.pos + 3 * (size_t)v;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+        if (pack.pos4) pack.pos4[v] = make_float4(x, y, z, 0.0f);
+    }
     const bool finite_pos = isfinite(x) && isfinite(y) && isfinite(z);
-    for (int b = 0; b < B; ++b) {
-        float4 r0, r1, r2, r3;
-        if (b < kStageViews) {
-            r0 = s_mvp[4 * b]; r1 = s_mvp[4 * b + 1]; r2 = s_mvp[4 * b + 2]; r3 = s_mvp[4 * b + 3];
-        } else {
-            const float4 *m4 = reinterpret_cast<const float4 *>(src.mvp) + 4 * b;
-            r0 = __ldg(m4); r1 = __ldg(m4 + 1); r2 = __ldg(m4 + 2); r3 = __ldg(m4 + 3);
-        }
-        float4 c;
-        c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
-        c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
-        c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
-        unsigned rxy = 0u;
-        float rzw = 0.0f;
-        if (r3.x == 0.0f && r3.y == 0.0f && r3.z == 0.0f && r3.w == 1.0f) {
-            // Orthographic view (uniform branch).  For a finite vertex the contract's w = ((0 x + 0 y) + 0 z) + 1 is
-            // exactly 1, so snap_rec's unit-w expressions apply as they are; for a non-finite one 0 * inf = NaN fails
-            // its w > 0 test -- the explicit finiteness test (once per vertex) stands in for that.
-            if (finite_pos && c.z >= -1.0f && c.z <= 1.0f) {
-                const float fx = c.x * (float)(8 * W), fy = c.y * (float)(8 * H);
-                if (fabsf(fx) <= kRecLimit && fabsf(fy) <= kRecLimit) {
-                    rxy = (unsigned)(__float2int_rn(fx) + addx) | ((unsigned)(__float2int_rn(fy) + addy) << 16);
-                    rzw = c.z;
-                }
+    uint2 *out = rec + (live ? v : 0);
+    for (int b0 = 0; b0 < B; b0 += kStageViews) {
+        const int nb = min(B - b0, kStageViews);
+        if (b0) __syncthreads();   // the previous group's rows are no longer read
+        for (int i = threadIdx.x; i < nb * 4; i += blockDim.x)
+            s_mvp[i] = __ldg(reinterpret_cast<const float4 *>(src.mvp) + 4 * b0 + i);
+        if (threadIdx.x < 32) {   // bit b: row 3 of view b0 + b is exactly (0 0 0 1)
+            bool unit = false;
+            if ((int)threadIdx.x < nb) {
+                const float4 r3 = __ldg(reinterpret_cast<const float4 *>(src.mvp) + 4 * (b0 + threadIdx.x) + 3);
+                unit = r3.x == 0.0f && r3.y == 0.0f && r3.z == 0.0f && r3.w == 1.0f;
             }
-        } else {
-            c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
-            snap_rec(c, W, H, addx, addy, rxy, rzw);
+            const unsigned bits = __ballot_sync(0xFFFFFFFFu, unit);
+            if (threadIdx.x == 0) s_unit = bits;
         }
-        rec[(size_t)b * src.V + v] = make_uint2(rxy, __float_as_uint(rzw));
+        __syncthreads();
+        if (!live) continue;
+        const unsigned unit_bits = s_unit;
+#pragma unroll 2
+        for (int b = 0; b < nb; ++b) {
+            const float4 r0 = s_mvp[4 * b], r1 = s_mvp[4 * b + 1], r2 = s_mvp[4 * b + 2];
+            float4 c;
+            c.x = ((r0.x * x + r0.y * y) + r0.z * z) + r0.w;
+            c.y = ((r1.x * x + r1.y * y) + r1.z * z) + r1.w;
+            c.z = ((r2.x * x + r2.y * y) + r2.z * z) + r2.w;
+            unsigned rxy = 0u;
+            float rzw = 0.0f;
+            if ((unit_bits >> b) & 1u) {
+                // Orthographic view (uniform branch).  For a finite vertex the contract's w = ((0 x + 0 y) + 0 z) + 1
+                // is exactly 1, so snap_rec's unit-w expressions apply as they are; for a non-finite one 0 * inf = NaN
+                // fails its w > 0 test -- the explicit finiteness test (once per vertex) stands in for that.
+                if (finite_pos && c.z >= -1.0f && c.z <= 1.0f) {
+                    const float fx = c.x * (float)(8 * W), fy = c.y * (float)(8 * H);
+                    if (fabsf(fx) <= kRecLimit && fabsf(fy) <= kRecLimit) {
+                        rxy = (unsigned)(__float2int_rn(fx) + addx) | ((unsigned)(__float2int_rn(fy) + addy) << 16);
+                        rzw = c.z;
+                    }
+                }
+            } else {
+                const float4 r3 = s_mvp[4 * b + 3];
+                c.w = ((r3.x * x + r3.y * y) + r3.z * z) + r3.w;
+                snap_rec(c, W, H, addx, addy, rxy, rzw);
+            }
+            *out = make_uint2(rxy, __float_as_uint(rzw));
+            out += src.V;
+        }
     }
 }
 
