@@ -156,6 +156,24 @@ def test_unprojection_in_texel_ranges_equals_one_pass(wr_ctx):
         fused_unproject(wr_ctx, pre, cam, 96, 96, geo, att, accum=part, add_to_accum=False, tex_range=(10, 5), **kw)
 
 
+def test_view_weights_are_re_read_when_the_tensor_changes(wr_ctx):
+    """The per-view blend weights arrive as a host tensor with every call; the device copy of an unchanged tensor is
+    reused, an in-place update (version counter) or another tensor is uploaded again."""
+    mesh, cam, images = _setup(wr_ctx.device)
+    proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    kw = dict(uv_size=128, poisson_blending=False, uv_padding=False, uv_exp_blend_alpha=3.0, aoi_cos_valid_threshold=0.2,
+              iou_rejection_threshold=None)
+    vw = torch.tensor([1.0, 0.5, 1.0, 2.0, 1.0, 1.0])
+    first = proj(img, mesh, cam, uv_exp_blend_view_weight=vw, **kw).clone()
+    again = proj(img, mesh, cam, uv_exp_blend_view_weight=vw, **kw)
+    assert torch.equal(first, again)
+    vw.mul_(torch.tensor([3.0, 1.0, 0.25, 1.0, 2.0, 1.0]))   # in place: same object, new version
+    changed = proj(img, mesh, cam, uv_exp_blend_view_weight=vw, **kw)
+    fresh = proj(img, mesh, cam, uv_exp_blend_view_weight=vw.clone(), **kw)
+    assert torch.equal(changed, fresh) and not torch.equal(changed, first)
+
+
 def test_unsupported_options_raise(wr_ctx):
     mesh, cam, images = _setup(wr_ctx.device)
     proj = wr.CameraProjection(None, None, str(wr_ctx.device), "cuda")

@@ -58,6 +58,12 @@ def test_camera_indexing_semantics():
     assert cam[1:3].w2c.shape == (2, 4, 4) and cam[[0, 5]].c2w.shape == (2, 4, 4)
     with pytest.raises(NotImplementedError):
         cam[(0, 1)]
+    # the matrices are row-major from the start (torch.linalg.inv returns column-major ones), also in a strided
+    # sub-batch: the operators then read them as they are, with no copy kernel in front of every call
+    for c in (cam, cam[::2], cam[[0, 5]], wr.get_camera(elevation_deg=[10.0] * 3, distance=[1.5] * 3, fovy_deg=[40.0] * 3,
+                                                       azimuth_deg=[0.0, 90.0, 200.0])):
+        assert c.w2c.is_contiguous() and c.mvp_mtx.is_contiguous() and c.proj_mtx.is_contiguous() and c.c2w.is_contiguous()
+    assert torch.equal(cam.w2c, torch.linalg.inv(cam.c2w))
     torch.manual_seed(0)
     a = torch.rand(1)
     torch.manual_seed(0)
