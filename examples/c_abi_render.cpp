@@ -48,6 +48,11 @@ int main(int argc, char **argv)
         !read_vec(f, w2c, (size_t)B * 16)) { fprintf(stderr, "short scene file\n"); return 1; }
     fclose(f);
 
+    if (wr_version() != WR_B200_ABI_VERSION) {   // a library built from another header: different argument structs
+        fprintf(stderr, "libwr_b200.so has ABI version %d, this program was compiled against %d\n", wr_version(),
+                WR_B200_ABI_VERSION);
+        return 4;
+    }
     wr_ctx *ctx = nullptr;
     int st = wr_ctx_create(0, &ctx);
     if (st != WR_OK) { fprintf(stderr, "wr_ctx_create: %s\n", wr_status_string(st)); return 3; }

@@ -61,6 +61,9 @@ typedef enum wr_status {
 const char *wr_status_string(int status);
 /* last CUDA error text recorded by this context (empty string if none) */
 const char *wr_ctx_last_error(const wr_ctx *ctx);
+/* Version of this header's ABI (struct layouts included).  wr_version() returns the value the LIBRARY was built with:
+ * a caller compiled against another header must not go on (its argument structs have a different layout). */
+#define WR_B200_ABI_VERSION 102
 int wr_version(void);
 
 /* One context per (device, stream in flight).  Not thread-safe, like the reference's contexts. */

@@ -210,6 +210,16 @@ def test_shared_library_exports_every_declared_symbol():
     assert L.wr_status_string(-5).decode() == "unsupported configuration"
 
 
+def test_abi_version_is_checked_at_load():
+    """The header, the library and the ctypes mirror carry one ABI version; a library of another version is refused
+    (its argument structs would be read with the wrong layout)."""
+    import re
+    from worldrenderer_b200 import _native
+    header = open(os.path.join(ROOT, "include", "wr_b200.h")).read()
+    assert int(re.search(r"#define WR_B200_ABI_VERSION (\d+)", header).group(1)) == _native.ABI_VERSION
+    assert _native.lib().wr_version() == _native.ABI_VERSION
+
+
 def test_library_is_sm100a_only_and_fmad_free_on_the_contract_path():
     from worldrenderer_b200 import build_native
     assert "-fmad=false" in build_native.NVCC_FLAGS

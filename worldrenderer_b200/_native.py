@@ -70,6 +70,7 @@ class UnprojectArgs(ctypes.Structure):
     ]
 
 
+ABI_VERSION = 102   # include/wr_b200.h WR_B200_ABI_VERSION (the ctypes structures below mirror that header)
 MAX_P2P_RANKS = 16
 
 
@@ -144,6 +145,9 @@ def lib() -> ctypes.CDLL:
     L.wr_view_scores.argtypes = [vp, vp, ci, vp, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, vp, vp, vp]
     L.wr_uv_padding.restype = ci
     L.wr_uv_padding.argtypes = [vp, vp, vp, ci, ci, ci, ci, vp, vp]
+    if L.wr_version() != ABI_VERSION:   # a stale library: its argument structs differ from the ones declared here
+        raise RuntimeError(f"{LIB_PATH} has ABI version {L.wr_version()}, this package expects {ABI_VERSION}: rebuild it "
+                           "with `python -m worldrenderer_b200.build_native --force`")
     _LIB = L
     return L
 

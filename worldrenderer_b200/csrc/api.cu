@@ -18,7 +18,7 @@ extern "C" const char *wr_status_string(int status)
     }
 }
 
-extern "C" int wr_version(void) { return 100; }
+extern "C" int wr_version(void) { return WR_B200_ABI_VERSION; }
 
 extern "C" const char *wr_ctx_last_error(const wr_ctx *ctx) { return ctx ? ctx->last_error : ""; }
 
