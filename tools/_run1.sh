@@ -1,4 +1,17 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python tools/unproj_rec_probe.py > gpurun_out/r02r_rec.log 2>&1
-cat gpurun_out/r02r_rec.log | tail -12
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r02u_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02u_tests.log
+tail -3 gpurun_out/r02u_tests.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02u_smoke.log 2>&1; tail -2 gpurun_out/r02u_smoke.log
+date +%s
+timeout 400 python bench.py > gpurun_out/bench_r02u.json 2> gpurun_out/bench_r02u.err; echo "bench rc=$?"
+date +%s
+timeout 200 python bench.py --impl reference > gpurun_out/bench_r02u_ref.json 2> gpurun_out/bench_r02u_ref.err; echo "ref rc=$?"
+date +%s
+python - <<'P'
+import json
+d=json.loads(open("gpurun_out/bench_r02u.json").read().strip().splitlines()[-1])
+print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["pipeline"]["frac"], d["stages_ms"], d["bake"]["ms_per_uv_bake_end_to_end"], d["config_d"]["views_per_s"], d["bake_sharded"]["ms_per_bake"])
+r=json.loads(open("gpurun_out/bench_r02u_ref.json").read().strip().splitlines()[-1])
+print(r["value"], r["config"]==d["config"])
+P
