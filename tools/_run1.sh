@@ -1,17 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/r02u_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r02u_tests.log
-tail -3 gpurun_out/r02u_tests.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02u_smoke.log 2>&1; tail -2 gpurun_out/r02u_smoke.log
-date +%s
-timeout 400 python bench.py > gpurun_out/bench_r02u.json 2> gpurun_out/bench_r02u.err; echo "bench rc=$?"
-date +%s
-timeout 200 python bench.py --impl reference > gpurun_out/bench_r02u_ref.json 2> gpurun_out/bench_r02u_ref.err; echo "ref rc=$?"
-date +%s
-python - <<'P'
-import json
-d=json.loads(open("gpurun_out/bench_r02u.json").read().strip().splitlines()[-1])
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["pipeline"]["frac"], d["stages_ms"], d["bake"]["ms_per_uv_bake_end_to_end"], d["config_d"]["views_per_s"], d["bake_sharded"]["ms_per_bake"])
-r=json.loads(open("gpurun_out/bench_r02u_ref.json").read().strip().splitlines()[-1])
-print(r["value"], r["config"]==d["config"])
-P
+timeout 240 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_r02_final_render python tools/prof_b.py > gpurun_out/r02v_ncu_render.log 2>&1; echo "rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/prof_r02_final_bake python tools/prof_bake.py > gpurun_out/r02v_ncu_bake.log 2>&1; echo "rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02_final.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r02v_ncu_list.log 2>&1; echo "rc=$?"
+ls -la gpurun_out/prof_r02_final_* gpurun_out/launches_r02_final.csv
