@@ -16,6 +16,28 @@ from worldrenderer_b200 import parallel
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+def test_chunk_bounds_partition_the_atlas_on_block_boundaries():
+    """Texel ranges of the chunked multi-GPU bake (sharded_bake(chunks=...)): a partition of the atlas, inner
+    boundaries on the exchange kernels' 1024-texel blocks, never an empty range -- every rank derives the same list
+    from (ntex, chunks, shape) alone, which is what makes the per-chunk device barriers pair up."""
+    for ntex in [1 << 16, 1000 * 1000, 1024 * 1024, 4096 * 4096, 1500 * 1500 + 4, 5000]:
+        for n in [1, 2, 3, 4, 8, 12, 64]:
+            for shape in ("equal", "falling"):
+                b = parallel.chunk_bounds(ntex, n, shape)
+                assert 1 <= len(b) <= n and b[0][0] == 0 and b[-1][1] == ntex
+                assert all(lo < hi for lo, hi in b)
+                assert all(b[i][1] == b[i + 1][0] and b[i][1] % 1024 == 0 for i in range(len(b) - 1))
+                sizes = [hi - lo for lo, hi in b]
+                if shape == "equal" and len(b) == n:
+                    assert max(sizes[:-1], default=0) - min(sizes[:-1], default=0) <= 1024
+                if shape == "falling":
+                    assert all(sizes[i] + 1024 >= sizes[i + 1] for i in range(len(sizes) - 2))
+    assert parallel.chunk_bounds(4096 * 4096, 8) == [(k << 21, (k + 1) << 21) for k in range(8)]
+    assert parallel.chunk_bounds(10 * 1024, 4, "falling") == [(0, 4096), (4096, 7168), (7168, 9216), (9216, 10240)]
+    with pytest.raises(ValueError):
+        parallel.chunk_bounds(1 << 20, 4, "rising")
+
+
 def test_shard_bounds_partition_everything_once():
     for n in [0, 1, 5, 6, 7, 32, 64]:
         for world in [1, 2, 3, 4, 8]:

@@ -278,16 +278,7 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
         # last exchange) put the large exchanges next to small unprojections and measured slower -- config E on
         # 8 x B200, chunks 4 / 6 / 8: falling 1.427 / 1.402 / 1.408 ms, equal 1.389 / 1.369 / 1.361 ms (one chunk: 1.703).
         # Boundaries on 1024 texels (the exchange kernels' blocks).
-        if chunk_shape not in ("falling", "equal"):
-            raise ValueError("chunk_shape must be 'falling' or 'equal'")
-        weights = [nchunks - k if chunk_shape == "falling" else 1 for k in range(nchunks)]
-        total_w = sum(weights)
-        bounds, lo = [], 0
-        for k in range(nchunks):
-            hi = ntex if k == nchunks - 1 else min(ntex, (lo + ntex * weights[k] // total_w + 1023) & ~1023)
-            if hi > lo:
-                bounds.append((lo, hi))
-            lo = hi
+        bounds = chunk_bounds(ntex, nchunks, chunk_shape)
         # a small exchange grid leaves the SMs to the unprojection: one block per SM for the multicast kernel (its best
         # anyway), two for the peer-load kernel (it needs more loads in flight)
         sms = torch.cuda.get_device_properties(ctx.device).multi_processor_count
@@ -325,6 +316,24 @@ def sharded_bake(ctx, mesh, cam_local: Camera, images_local: torch.Tensor, uv_si
                                   poisson_blending=poisson_blending, pb_solver=pb_solver, pb_num_iters=pb_num_iters,
                                   pb_keep_original_border=pb_keep_original_border)
     return atlas, valid_any
+
+
+def chunk_bounds(ntex: int, nchunks: int, shape: str = "equal") -> List[Tuple[int, int]]:
+    """Texel ranges [lo, hi) of a chunked bake: a partition of range(ntex) into at most `nchunks` non-empty ranges whose
+    inner boundaries are multiples of 1024 texels (the exchange kernels' blocks).  shape "equal": equal sizes;
+    "falling": sizes K : K-1 : ... : 1 (a small last exchange)."""
+    if shape not in ("falling", "equal"):
+        raise ValueError("chunk_shape must be 'falling' or 'equal'")
+    nchunks = max(1, int(nchunks))
+    weights = [nchunks - k if shape == "falling" else 1 for k in range(nchunks)]
+    total_w = sum(weights)
+    bounds, lo = [], 0
+    for k in range(nchunks):
+        hi = ntex if k == nchunks - 1 else min(ntex, (lo + ntex * weights[k] // total_w + 1023) & ~1023)
+        if hi > lo:
+            bounds.append((lo, hi))
+        lo = hi
+    return bounds
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
