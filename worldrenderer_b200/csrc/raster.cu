@@ -129,7 +129,7 @@ __device__ __forceinline__ void raster_small(int x0, int y0, int x1, int y1, int
     const int bias0 = top_left(dx0, dy0) ? 0 : 1;
     const int bias1 = top_left(dx1, dy1) ? 0 : 1;
     const int bias2 = top_left(dx2, dy2) ? 0 : 1;
-    const float inv_area = 1.0f / __int2float_rn(area2);
+    const float inv_area = wr_rcp_int(area2);
     const int px0 = 16 * c0, py0 = 16 * r0;  // snapped coordinates are relative to the sample of pixel (0, 0)
     int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
     int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
@@ -329,6 +329,7 @@ struct MvParams {
     const int32_t *tri;            // [F,3]
     int F, V, B, Bq;
     int W, H;
+    unsigned HW;                   // H * W (<= 2048^2 on this path): a view's offset into `depth` is one wide multiply
     unsigned lo_px, hi_px;         // packed (row << 16 | col) first / last pixel of the viewport in biased pixel units
     unsigned long long *depth;     // [B,H,W]
     uint32_t *queue;               // [B,Fq]
@@ -472,7 +473,7 @@ __device__ __forceinline__ void mv_single(const MvParams &P, unsigned xy0, unsig
     const int m = __vimin3_s32(F0, F1, F2);
     if (m < 0) return;
     if (m == 0 && !mv_tie_break(a0, b0, a1, b1, a2, b2, F0, F1, F2, flip)) return;
-    const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
+    const float inv_area = wr_rcp_int(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
     const float w0 = __int2float_rn(E0) * inv_area;
     const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
     const float w2 = (1.0f - w0) - w1;
@@ -512,7 +513,7 @@ __device__ __forceinline__ void mv_fast(const MvParams &P, unsigned xy0, unsigne
     const int E0 = u1 * v2 - u2 * v1, E1 = u2 * v0 - u0 * v2, E2 = u0 * v1 - u1 * v0;
     const int area2 = E0 + E1 + E2;
     const bool flip = lo < 0;
-    const float inv_area = 1.0f / __int2float_rn(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
+    const float inv_area = wr_rcp_int(area2);   // signed: float(E) * inv_area == float(F) * (1 / |area|)
     const float w0 = __int2float_rn(E0) * inv_area;
     const float w1 = __int2float_rn(flip ? E2 : E1) * inv_area;
     const float w2 = (1.0f - w0) - w1;
@@ -562,7 +563,7 @@ __device__ __forceinline__ void mv_multi(const MvParams &P, unsigned xy0, unsign
     const int bias1 = top_left(dx1, dy1) ? 0 : 1;
     const int bias2 = top_left(dx2, dy2) ? 0 : 1;
     const float za = flip ? z2 : z1, zb = flip ? z1 : z2;
-    const float inv_area = 1.0f / __int2float_rn(area2);
+    const float inv_area = wr_rcp_int(area2);
     const int px0 = 16 * c0, py0 = 16 * r0;
     int e0r = dx0 * (py0 - y1) - dy0 * (px0 - x1);
     int e1r = dx1 * (py0 - y2) - dy1 * (px0 - x2);
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(256, WR_MV_MINB) k_setup_mv(MvParams P, Raster
                 mv_cold(Pold, src, b, i0, i1, i2, t, P.depth + (size_t)b * P.H * P.W, push, entry);
             } else if ((tt & kGuard) == kGuard) {
                 const float z0 = __uint_as_float(ra.y), z1 = __uint_as_float(rc.y), z2 = __uint_as_float(rd.y);
-                unsigned long long *depth_view = P.depth + (size_t)b * P.H * P.W;
+                unsigned long long *depth_view = P.depth + (unsigned long long)(unsigned)b * P.HW;
                 const unsigned mn = __vimin3_u16x2(a, c, d), mx = __vimax3_u16x2(a, c, d);
                 if (((mx - mn) & 0xFFE0FFE0u) == 0u) {
                     // spans less than two pixels: 1, 2 or 2 x 2 samples
@@ -1240,7 +1241,7 @@ int wr_run_raster(wr_ctx *ctx, const VtxSrc &src, int B, const int32_t *tri, int
             MvParams M;
             uint2 *rec = reinterpret_cast<uint2 *>(sv);
             M.rec = rec; M.tri = tri; M.F = F; M.V = V; M.B = B; M.Bq = B;
-            M.W = W; M.H = H;
+            M.W = W; M.H = H; M.HW = (unsigned)H * (unsigned)W;
             const int lo_c = 2048 - W / 2, lo_r = 2048 - H / 2;
             M.lo_px = (unsigned)lo_c | ((unsigned)lo_r << 16);
             M.hi_px = (unsigned)(lo_c + W - 1) | ((unsigned)(lo_r + H - 1) << 16);
