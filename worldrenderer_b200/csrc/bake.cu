@@ -55,6 +55,20 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, i
 constexpr int kPrepTW = 32, kPrepTH = 32;  // output tile per block
 constexpr int kPrepBH = 8;                 // block = 32 x 8 threads, four output rows per thread
 
+// Maximum of n values STRIDE apart (one direction of the separable max-pool).  The reference's default window
+// (depth_grad_dilation = 5, projection.py:77) is unrolled: five loads and two three-input maxima instead of a counted
+// loop of load / max / increment / compare / branch -- a sixth of this issue-bound kernel's instructions.  The maximum
+// does not depend on the order (the values are >= 0 or -inf, never -0; fmaxf drops a NaN whichever way round).
+template <int STRIDE>
+__device__ __forceinline__ float window_max(const float *p, int n)
+{
+    if (n == 5)
+        return fmaxf(fmaxf(fmaxf(p[0], p[STRIDE]), p[2 * STRIDE]), fmaxf(p[3 * STRIDE], p[4 * STRIDE]));
+    float m = p[0];
+    for (int k = 1; k < n; ++k) m = fmaxf(m, p[k * STRIDE]);
+    return m;
+}
+
 __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *normal, const uint8_t *mask,
                                                                 const float *depth, const float *position,
                                                                 const float *w2c, const float *images, int H, int W,
@@ -131,9 +145,7 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
         __syncthreads();
         for (int ry = threadIdx.y; ry < gh; ry += kPrepBH) {  // row maxima: one output column per thread
             const float *row = s_g + ry * gw + threadIdx.x;
-            float m = row[0];
-            for (int k = 1; k < dilation; ++k) m = fmaxf(m, row[k]);
-            s_r[ry * kPrepTW + threadIdx.x] = m;
+            s_r[ry * kPrepTW + threadIdx.x] = window_max<1>(row, dilation);
         }
         __syncthreads();
     }
@@ -148,8 +160,7 @@ __global__ void __launch_bounds__(kPrepTW * kPrepBH) k_view_prep(const float *no
         float dg = 0.0f;
         if (dilation > 0) {
             const float *col = s_r + ty * kPrepTW + threadIdx.x;
-            dg = col[0];
-            for (int k = 1; k < dilation; ++k) dg = fmaxf(dg, col[k * kPrepTW]);
+            dg = window_max<kPrepTW>(col, dilation);
             if (depth_grad) depth_grad[o] = dg;
         }
         if (attr_map) {
