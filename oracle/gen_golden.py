@@ -360,6 +360,58 @@ def smart_paint_case(mu):
           "top-2 margins", [float(np.sort(s)[-1] - np.sort(s)[-2]) for s in rec["scores"]])
 
 
+def strategy_cases(mu):
+    """The validity / blend-weight strategy classes (uv.py:248-370) on synthetic per-view tensors: every option the
+    reference's callers can reach -- depth-gradient threshold with and without a gradient map, view masks present /
+    absent, first_view_dominate, per-view weights, linear and softmax normalisation."""
+    import contextlib
+    import io
+    rng = np.random.default_rng(11)
+    nv, h, w = 5, 24, 20
+    geo_in = dict(uv_pos_error=(rng.random((nv, h, w)) ** 4 * 4e-3).astype(np.float32),
+                  uv_aoi_cos=(rng.random((nv, h, w)) * 1.2 - 0.2).astype(np.float32),
+                  uv_depth_grad=(rng.random((nv, h, w)) * 0.25).astype(np.float32))
+    uv_mask = rng.random((h, w)) < 0.8
+    uv_mask_proj = (rng.random((nv, h, w)) ** 0.1).astype(np.float32)   # mostly foreground
+    view_weight = np.array([1.0, 0.5, 2.0, 1.0, 3.0], np.float32)
+    out = dict(geo_in, uv_mask=uv_mask, uv_mask_proj=uv_mask_proj, view_weight=view_weight)
+
+    def geo(with_grad=True):
+        z = torch.zeros(1)
+        return mu.uv.UVRenderGeometryOutput(
+            uv_pos_proj=z, uv_pos_error=torch.from_numpy(geo_in["uv_pos_error"]),
+            uv_aoi_cos=torch.from_numpy(geo_in["uv_aoi_cos"]), uv_pos_ndc=z, view_mask=z, view_normal=z,
+            view_aoi_cos=z, view_position=z, view_depth=z,
+            uv_depth_grad=torch.from_numpy(geo_in["uv_depth_grad"]) if with_grad else None)
+
+    pre = mu.uv.UVPrecomputeOutput(height=h, width=w, uv_attr=torch.zeros(h, w, 3), uv_mask=torch.from_numpy(uv_mask),
+                                   uv_pos=torch.zeros(h, w, 3))
+    attr = mu.uv.UVRenderAttrOutput(uv_attr_proj=torch.zeros(1), uv_mask_proj=torch.from_numpy(uv_mask_proj))
+    attr_nomask = mu.uv.UVRenderAttrOutput(uv_attr_proj=torch.zeros(1), uv_mask_proj=None)
+    validity = {   # name -> (constructor kwargs, gradient map present, view masks present)
+        "v_default": (dict(), True, True),
+        "v_thresholds": (dict(pos_error_eps=5e-4, aoi_cos_thresh=0.3, mask_thresh=0.5, depth_grad_thresh=0.1), True, True),
+        "v_grad_missing": (dict(depth_grad_thresh=0.1), False, True),
+        "v_no_view_mask": (dict(aoi_cos_thresh=0.2, depth_grad_thresh=0.15), True, False),
+        "v_first_view": (dict(aoi_cos_thresh=0.2, first_view_dominate=True), True, True),
+    }
+    with contextlib.redirect_stdout(io.StringIO()):   # the reference prints a warning in two of the cases
+        for name, (kw, with_grad, with_mask) in validity.items():
+            v = mu.uv.SimpleUVValidityStrategy(**kw)(pre, geo(with_grad), attr if with_mask else attr_nomask)
+            out[name] = _np(v)
+    valid = torch.from_numpy(out["v_default"])
+    blends = {
+        "w_linear_a1": dict(alpha=1.0),
+        "w_linear_a3": dict(alpha=3.0),
+        "w_linear_a6_vw": dict(alpha=6.0, view_weight=torch.from_numpy(view_weight)),
+        "w_softmax_a2": dict(alpha=2.0, normalization="softmax"),
+        "w_softmax_a3_vw": dict(alpha=3.0, normalization="softmax", view_weight=torch.from_numpy(view_weight)),
+    }
+    for name, kw in blends.items():
+        out[name] = _np(mu.uv.ExponentialBlend(**kw)(pre, geo(), attr, valid.clone()))
+    np.savez_compressed(os.path.join(OUT, "strategies.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -374,6 +426,7 @@ def main():
     smart_paint_case(mu)
     operator_cases(mu)
     tangent_cases(mu)
+    strategy_cases(mu)
     for n in sorted(os.listdir(OUT)):
         print(n, os.path.getsize(os.path.join(OUT, n)))
 

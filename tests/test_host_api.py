@@ -288,3 +288,60 @@ def test_camera_projection_needs_a_solver_for_poisson_blending():
     # the reference's defaults are kept (projection.py:54-83): Poisson blending and seam padding are ON by default
     assert sig.parameters["poisson_blending"].default is True and sig.parameters["uv_padding"].default is True
     assert sig.parameters["pb_num_iters"].default == 1000 and sig.parameters["uv_size"].default == 2048
+
+
+def test_validity_and_blend_strategies_match_reference(capsys):
+    """SimpleUVValidityStrategy / ExponentialBlend (uv.py:248-348) are caller-visible strategy objects that run on
+    tensors (the step-by-step API; the fused bake implements the default pair in its kernel).  Recordings of the
+    reference's own classes (oracle/gen_golden.py strategy_cases): every option -- thresholds, a missing gradient map,
+    no view masks, first_view_dominate, per-view weights, linear and softmax normalisation."""
+    from worldrenderer_b200 import uv
+    g = dict(np.load(os.path.join(GOLDEN, "strategies.npz")))
+    nv, h, w = g["uv_aoi_cos"].shape
+    z = torch.zeros(1)
+
+    def geo(with_grad=True):
+        return uv.UVRenderGeometryOutput(
+            uv_pos_proj=z, uv_pos_error=torch.from_numpy(g["uv_pos_error"]), uv_aoi_cos=torch.from_numpy(g["uv_aoi_cos"]),
+            uv_pos_ndc=z, view_mask=z, view_normal=z, view_aoi_cos=z, view_position=z, view_depth=z,
+            uv_depth_grad=torch.from_numpy(g["uv_depth_grad"]) if with_grad else None)
+
+    pre = uv.UVPrecomputeOutput(height=h, width=w, uv_attr=torch.zeros(h, w, 3), uv_mask=torch.from_numpy(g["uv_mask"]),
+                                uv_pos=torch.zeros(h, w, 3))
+    attr = uv.UVRenderAttrOutput(uv_attr_proj=z, uv_mask_proj=torch.from_numpy(g["uv_mask_proj"]))
+    attr_nomask = uv.UVRenderAttrOutput(uv_attr_proj=z, uv_mask_proj=None)
+    validity = {
+        "v_default": (dict(), True, True),
+        "v_thresholds": (dict(pos_error_eps=5e-4, aoi_cos_thresh=0.3, mask_thresh=0.5, depth_grad_thresh=0.1), True, True),
+        "v_grad_missing": (dict(depth_grad_thresh=0.1), False, True),
+        "v_no_view_mask": (dict(aoi_cos_thresh=0.2, depth_grad_thresh=0.15), True, False),
+        "v_first_view": (dict(aoi_cos_thresh=0.2, first_view_dominate=True), True, True),
+    }
+    for name, (kw, with_grad, with_mask) in validity.items():
+        got = uv.SimpleUVValidityStrategy(**kw)(pre, geo(with_grad), attr if with_mask else attr_nomask)
+        assert got.dtype == torch.bool
+        np.testing.assert_array_equal(got.numpy(), g[name], err_msg=name)
+    printed = capsys.readouterr().out   # the reference's two warnings are part of its behaviour
+    assert "Depth gradient is not computed" in printed and "No view mask provided" in printed
+    assert g["v_first_view"][1:].sum() < g["v_default"][1:].sum() and not (g["v_first_view"][1:] & g["v_first_view"][:1]).any()
+
+    vw = torch.from_numpy(g["view_weight"])
+    blends = {
+        "w_linear_a1": dict(alpha=1.0),
+        "w_linear_a3": dict(alpha=3.0),
+        "w_linear_a6_vw": dict(alpha=6.0, view_weight=vw),
+        "w_softmax_a2": dict(alpha=2.0, normalization="softmax"),
+        "w_softmax_a3_vw": dict(alpha=3.0, normalization="softmax", view_weight=vw),
+    }
+    valid = torch.from_numpy(g["v_default"])
+    for name, kw in blends.items():
+        got = uv.ExponentialBlend(**kw)(pre, geo(), attr, valid.clone())
+        np.testing.assert_allclose(got.numpy(), g[name], rtol=1e-6, atol=1e-7, err_msg=name)
+    with pytest.raises(ValueError):
+        uv.ExponentialBlend(normalization="max")(pre, geo(), attr, valid.clone())
+    # RandomChoiceBlend: one view per texel, and a valid one wherever the texel has any
+    rc = uv.RandomChoiceBlend(alpha=1.0)(pre, geo(), attr, valid.clone())
+    assert rc.shape == (nv, h, w) and torch.equal(rc.sum(0), torch.ones(h, w))
+    pick = rc.argmax(0)
+    has = valid.any(0) & (torch.from_numpy(g["uv_aoi_cos"]) * valid).gt(0).any(0)
+    assert bool(valid.gather(0, pick[None])[0][has].all())
