@@ -139,6 +139,34 @@ def test_accumulate_then_finalize_equals_fused(wr_ctx):
     torch.testing.assert_close(out, full, rtol=1e-5, atol=1e-6)
 
 
+def test_fused_unprojection_with_first_view_dominate_equals_stepwise(wr_ctx):
+    """wr_unproject_args.first_view_dominate (SimpleUVValidityStrategy(first_view_dominate=True), uv.py:294-296): a
+    texel the first view sees is taken from that view alone.  The fused kernel against the step-by-step API, whose
+    strategy objects are pinned to the reference on CPU (tests/test_host_api.py)."""
+    from worldrenderer_b200.uv import fused_unproject, fused_view_maps
+    mesh, cam, images = _setup(wr_ctx.device)
+    pre = wr.uv_precompute(wr_ctx, mesh, 128, 128)
+    img = torch.from_numpy(images).to(wr_ctx.device)
+    # no depth-gradient threshold: at 96^2 it confines every view of the six-view rig to a 45-degree cap and the
+    # views would not overlap at all
+    kw = dict(aoi_cos_thresh=0.2, depth_grad_thresh=None, alpha=3.0)
+    _, geo_m, att_m = fused_view_maps(wr_ctx, mesh, cam, img, 96, 96, 5)
+    fused, fused_any, _, _, _ = fused_unproject(wr_ctx, pre, cam, 96, 96, geo_m, att_m, first_view_dominate=True, **kw)
+    plain, plain_any, _, _, _ = fused_unproject(wr_ctx, pre, cam, 96, 96, geo_m, att_m, **kw)
+    geo = wr.uv_render_geometry(wr_ctx, mesh, cam, 96, 96, pre, compute_depth_grad=True, depth_grad_dilation=5)
+    attr = wr.uv_render_attr(torch.from_numpy(images), geo)
+    strategy = wr.SimpleUVValidityStrategy(aoi_cos_thresh=0.2, first_view_dominate=True)
+    blend = wr.uv_blend(pre, geo, attr, uv_validity_strategy=strategy,
+                        uv_blend_weight_strategy=wr.ExponentialBlend(alpha=3.0), do_uv_padding=False)
+    assert torch.equal(fused_any, blend.uv_valid_mask_blend)
+    torch.testing.assert_close(fused, blend.uv_attr_blend, rtol=RTOL, atol=ATOL)
+    # the option is live: same coverage (a texel of view 0 is still covered), other colours where views overlap
+    assert torch.equal(fused_any, plain_any)
+    first = blend.uv_valid_mask[0]
+    assert bool(first.any()) and not bool((blend.uv_valid_mask[1:] & first[None]).any())
+    assert float((fused - plain).abs().max()) > 1e-3
+
+
 def test_unprojection_in_texel_ranges_equals_one_pass(wr_ctx):
     """wr_uv_unproject over texel ranges (what the chunked multi-GPU bake issues) fills the same accumulators."""
     from worldrenderer_b200.uv import fused_unproject, fused_view_maps
