@@ -147,3 +147,33 @@ def test_bake_intermediates_match_reference():
     np.testing.assert_allclose(geo["view_depth_grad"], g["view_depth_grad"], rtol=1e-4, atol=1e-3)
     err_ok = np.isclose(geo["uv_pos_error"][:, inside], g["uv_pos_error"][:, inside], rtol=1e-3, atol=1e-5)
     assert err_ok.mean() > 0.999
+
+
+def test_validity_and_blend_restatements_match_reference_strategies():
+    """oracle uv_validity / exponential_blend against recordings of the reference's SimpleUVValidityStrategy and
+    ExponentialBlend (uv.py:248-348) with every option (gen_golden.py strategy_cases)."""
+    g = dict(np.load(os.path.join(GOLDEN, "strategies.npz")))
+    pre = {"uv_mask": g["uv_mask"]}
+    geo = {k: g[k] for k in ("uv_pos_error", "uv_aoi_cos", "uv_depth_grad")}
+    geo_nograd = dict(geo, uv_depth_grad=None)
+    attr = {"uv_mask_proj": g["uv_mask_proj"]}
+    cases_ = {
+        "v_default": (dict(), geo, attr),
+        "v_thresholds": (dict(pos_error_eps=5e-4, aoi_cos_thresh=0.3, mask_thresh=0.5, depth_grad_thresh=0.1), geo, attr),
+        "v_grad_missing": (dict(depth_grad_thresh=0.1), geo_nograd, attr),
+        "v_no_view_mask": (dict(aoi_cos_thresh=0.2, depth_grad_thresh=0.15), geo, {"uv_mask_proj": None}),
+        "v_first_view": (dict(aoi_cos_thresh=0.2, first_view_dominate=True), geo, attr),
+    }
+    for name, (kw, ge, at) in cases_.items():
+        np.testing.assert_array_equal(render_oracle.uv_validity(pre, ge, at, **kw), g[name], err_msg=name)
+    valid = g["v_default"]
+    blends = {
+        "w_linear_a1": dict(alpha=1.0),
+        "w_linear_a3": dict(alpha=3.0),
+        "w_linear_a6_vw": dict(alpha=6.0, view_weight=g["view_weight"]),
+        "w_softmax_a2": dict(alpha=2.0, normalization="softmax"),
+        "w_softmax_a3_vw": dict(alpha=3.0, normalization="softmax", view_weight=g["view_weight"]),
+    }
+    for name, kw in blends.items():
+        got = render_oracle.exponential_blend(geo, valid.copy(), **kw)
+        np.testing.assert_allclose(got, g[name], rtol=2e-6, atol=1e-7, err_msg=name)
